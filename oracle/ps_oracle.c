@@ -1,0 +1,313 @@
+/*
+ * ps_oracle.c -- CPU restatement of the parameter-server update semantics that
+ * douban/tfmesos selects for its data path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` legs may load this file's shared object.  Nothing under
+ * tfmesos_b200/ links, imports or executes it: the product path is the CUDA
+ * library (include/psx.h) and it fails loudly when that library is missing.
+ *
+ * PARITY UNPINNED upstream: the reference ships no test, golden vector or
+ * known-answer value for this path (tox.ini:8 runs flake8 only; the sole
+ * expected output in the tree is "42", README.rst:65).  The arithmetic lives in
+ * TensorFlow (requirements.txt:10 pins tensorflow-gpu==0.12.0), which is not
+ * vendored under /root/reference and cannot be installed here.  What is
+ * restated below is TF 0.12's published kernel algebra:
+ *
+ *   ApplyGradientDescent   var -= grad * lr
+ *   ApplyAdam              alpha = lr * sqrt(1 - b2^t) / (1 - b1^t)
+ *                          m   += (g - m)   * (1 - b1)
+ *                          v   += (g*g - v) * (1 - b2)
+ *                          var -= (m * alpha) / (sqrt(v) + eps)
+ *   AdamOptimizer._finish  b1^t *= b1 ; b2^t *= b2   (once per minimize())
+ *
+ * anchored on the reference's own call sites:
+ *   examples/mnist/mnist.py:55               GradientDescentOptimizer(0.005)
+ *   examples/mnist/mnist_replica.py:147-157  AdamOptimizer(lr) [+ SyncReplicas]
+ *   examples/matrix_factorization.py:39-41   GradientDescentOptimizer(0.1)
+ *   tfmesos/server.py:52-61                  tf.train.Server  (PS on host CPU)
+ *
+ * All arithmetic is IEEE-754 binary32, one rounding per operation, never
+ * contracted to FMA (build with -ffp-contract=off), which is what Eigen's
+ * un-fused CPU expressions produce and what the CUDA kernels reproduce with
+ * -fmad=false -prec-div=true -prec-sqrt=true.  Hence the GPU parity bar for
+ * these functions is BIT-EXACT, not a tolerance.
+ *
+ * Update disciplines:
+ *   PSX_ORACLE_ASYNC_ORDERED  every worker's push is applied on its own, in
+ *                             worker-index order (the serialisable schedule of
+ *                             the reference's default async mode)
+ *   PSX_ORACLE_SUM            g = ((g0 + g1) + g2) + ...   then one apply
+ *   PSX_ORACLE_SYNC_MEAN      g = sum / (float)W           then one apply
+ *                             (SyncReplicasOptimizer, mnist_replica.py:148-154)
+ */
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <pthread.h>
+#include <unistd.h>
+
+enum { PSX_ORACLE_ASYNC_ORDERED = 0, PSX_ORACLE_SUM = 1, PSX_ORACLE_SYNC_MEAN = 2 };
+
+/* ---- single applies (mnist.py:55 / matrix_factorization.py:39) ------------ */
+
+void psx_oracle_sgd(float *var, const float *g, size_t n, float lr)
+{
+    for (size_t i = 0; i < n; ++i) {
+        float step = g[i] * lr;
+        var[i] = var[i] - step;
+    }
+}
+
+/* alpha exactly as TF's functor spells it: (lr * sqrt(1-b2p)) / (1-b1p) */
+float psx_oracle_adam_alpha(float lr, float b1p, float b2p)
+{
+    float s = sqrtf(1.0f - b2p);
+    float num = lr * s;
+    return num / (1.0f - b1p);
+}
+
+/* one ApplyAdam over n elements with the STORED powers; does not advance them
+ * (mnist_replica.py:147) */
+void psx_oracle_adam(float *var, float *m, float *v, const float *g, size_t n,
+                     float lr, float b1, float b2, float eps, float b1p, float b2p)
+{
+    const float alpha = psx_oracle_adam_alpha(lr, b1p, b2p);
+    const float omb1 = 1.0f - b1;
+    const float omb2 = 1.0f - b2;
+    for (size_t i = 0; i < n; ++i) {
+        float gi = g[i];
+        float mi = m[i];
+        float vi = v[i];
+        float dm = (gi - mi) * omb1;
+        mi = mi + dm;
+        float g2 = gi * gi;
+        float dv = (g2 - vi) * omb2;
+        vi = vi + dv;
+        float num = mi * alpha;
+        float den = sqrtf(vi) + eps;
+        var[i] = var[i] - num / den;
+        m[i] = mi;
+        v[i] = vi;
+    }
+}
+
+/* ---- one PS round over W gradient slots ----------------------------------- */
+/* slots: W contiguous gradients of n floats each (slot w at slots + w*stride).
+ * state[0]=b1^t, state[1]=b2^t (Adam only), advanced here exactly as
+ * AdamOptimizer._finish does; *step is the global_step counter
+ * (mnist.py:46,55; mnist_replica.py:121,156-157). */
+
+static void reduce_slots(float *dst, const float *slots, size_t stride, int W,
+                         size_t n, int mean)
+{
+    for (size_t i = 0; i < n; ++i) {
+        float acc = slots[i];
+        for (int w = 1; w < W; ++w)
+            acc = acc + slots[(size_t)w * stride + i];
+        if (mean)
+            acc = acc / (float)W;
+        dst[i] = acc;
+    }
+}
+
+int psx_oracle_round_sgd(float *var, const float *slots, size_t stride, int W,
+                         size_t n, float lr, int mode, float *scratch,
+                         int64_t *step)
+{
+    if (W < 1)
+        return -1;
+    if (mode == PSX_ORACLE_ASYNC_ORDERED) {
+        for (int w = 0; w < W; ++w)
+            psx_oracle_sgd(var, slots + (size_t)w * stride, n, lr);
+        *step += W;
+        return 0;
+    }
+    reduce_slots(scratch, slots, stride, W, n, mode == PSX_ORACLE_SYNC_MEAN);
+    psx_oracle_sgd(var, scratch, n, lr);
+    *step += 1;
+    return 0;
+}
+
+int psx_oracle_round_adam(float *var, float *m, float *v, const float *slots,
+                          size_t stride, int W, size_t n, float lr, float b1,
+                          float b2, float eps, int mode, float *state,
+                          float *scratch, int64_t *step)
+{
+    if (W < 1)
+        return -1;
+    if (mode == PSX_ORACLE_ASYNC_ORDERED) {
+        for (int w = 0; w < W; ++w) {
+            psx_oracle_adam(var, m, v, slots + (size_t)w * stride, n, lr, b1, b2,
+                            eps, state[0], state[1]);
+            state[0] = state[0] * b1;
+            state[1] = state[1] * b2;
+        }
+        *step += W;
+        return 0;
+    }
+    reduce_slots(scratch, slots, stride, W, n, mode == PSX_ORACLE_SYNC_MEAN);
+    psx_oracle_adam(var, m, v, scratch, n, lr, b1, b2, eps, state[0], state[1]);
+    state[0] = state[0] * b1;
+    state[1] = state[1] * b2;
+    *step += 1;
+    return 0;
+}
+
+/* ---- bf16 wire format (BASELINE config #4: grads pushed / params pulled bf16)
+ * round-to-nearest-even float -> bf16, NaN kept quiet; matches
+ * __float2bfloat16_rn on the device. */
+uint16_t psx_oracle_f32_to_bf16(float f)
+{
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u)
+        return (uint16_t)((u >> 16) | 0x0040u);
+    uint32_t lsb = (u >> 16) & 1u;
+    u += 0x7fffu + lsb;
+    return (uint16_t)(u >> 16);
+}
+
+float psx_oracle_bf16_to_f32(uint16_t h)
+{
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+
+void psx_oracle_cast_f32_bf16(uint16_t *dst, const float *src, size_t n)
+{
+    for (size_t i = 0; i < n; ++i)
+        dst[i] = psx_oracle_f32_to_bf16(src[i]);
+}
+
+void psx_oracle_cast_bf16_f32(float *dst, const uint16_t *src, size_t n)
+{
+    for (size_t i = 0; i < n; ++i)
+        dst[i] = psx_oracle_bf16_to_f32(src[i]);
+}
+
+/* ---- multi-threaded CPU-PS round: the timed CPU baseline ------------------
+ * The reference's CPU path per worker-step: PULL = the PS
+ * copies every variable out to the worker (one RecvTensor per variable),
+ * PUSH = the worker's gradient is copied into the PS, APPLY on PS host cores
+ * (Eigen thread pool).  This is the best case for that path: both transfers
+ * are plain memcpy (no protobuf, no TCP) and the apply is spread over every
+ * host thread, element range by element range; per element the arithmetic is
+ * the scalar code above, so results equal the single-thread functions bit for
+ * bit.  worker_grad[w] / worker_param[w] are the workers' private buffers. */
+
+static void range_of(size_t n, int part, int parts, size_t *lo, size_t *hi)
+{
+    size_t chunk = (n + (size_t)parts - 1) / (size_t)parts;
+    chunk = (chunk + 15) & ~(size_t)15;
+    *lo = (size_t)part * chunk;
+    *hi = *lo + chunk;
+    if (*lo > n) *lo = n;
+    if (*hi > n) *hi = n;
+}
+
+int psx_oracle_threads(void)
+{
+    long n = sysconf(_SC_NPROCESSORS_ONLN);
+    if (n < 1) n = 1;
+    if (n > 256) n = 256;
+    return (int)n;
+}
+
+typedef struct {
+    float *var, *m, *v, *slots, *scratch;
+    size_t stride, n;
+    float *const *worker_grad;
+    float *const *worker_param;
+    int W, opt_adam, mode, part, parts;
+    float lr, b1, b2, eps;
+    const float *b1p, *b2p;
+} cpu_ps_job;
+
+static void *cpu_ps_part(void *arg)
+{
+    cpu_ps_job *j = (cpu_ps_job *)arg;
+    size_t lo, hi;
+    range_of(j->n, j->part, j->parts, &lo, &hi);
+    size_t cnt = hi - lo;
+    if (cnt == 0)
+        return NULL;
+    /* PUSH: worker -> PS receive buffers */
+    for (int w = 0; w < j->W; ++w)
+        memcpy(j->slots + (size_t)w * j->stride + lo, j->worker_grad[w] + lo, cnt * 4);
+    /* APPLY on the PS */
+    if (j->mode == PSX_ORACLE_ASYNC_ORDERED) {
+        for (int w = 0; w < j->W; ++w) {
+            const float *g = j->slots + (size_t)w * j->stride + lo;
+            if (j->opt_adam)
+                psx_oracle_adam(j->var + lo, j->m + lo, j->v + lo, g, cnt, j->lr,
+                                j->b1, j->b2, j->eps, j->b1p[w], j->b2p[w]);
+            else
+                psx_oracle_sgd(j->var + lo, g, cnt, j->lr);
+        }
+    } else {
+        reduce_slots(j->scratch + lo, j->slots + lo, j->stride, j->W, cnt,
+                     j->mode == PSX_ORACLE_SYNC_MEAN);
+        if (j->opt_adam)
+            psx_oracle_adam(j->var + lo, j->m + lo, j->v + lo, j->scratch + lo, cnt,
+                            j->lr, j->b1, j->b2, j->eps, j->b1p[0], j->b2p[0]);
+        else
+            psx_oracle_sgd(j->var + lo, j->scratch + lo, cnt, j->lr);
+    }
+    /* PULL: PS -> every worker */
+    for (int w = 0; w < j->W; ++w)
+        memcpy(j->worker_param[w] + lo, j->var + lo, cnt * 4);
+    return NULL;
+}
+
+/* threads <= 0: one per online core, but never less than 64 Ki elements each */
+int psx_oracle_cpu_ps_round(float *var, float *m, float *v, float *slots,
+                            size_t stride, float *const *worker_grad,
+                            float *const *worker_param, int W, size_t n,
+                            int opt_adam, float lr, float b1, float b2, float eps,
+                            int mode, float *state, float *scratch, int64_t *step,
+                            int threads)
+{
+    if (W < 1)
+        return -1;
+    if (W > 64)
+        return -2;
+    int parts = threads > 0 ? threads : psx_oracle_threads();
+    size_t cap = n / 65536 + 1;
+    if ((size_t)parts > cap) parts = (int)cap;
+    if (parts > 256) parts = 256;
+    float b1p[64], b2p[64];
+    b1p[0] = opt_adam ? state[0] : 0.0f;
+    b2p[0] = opt_adam ? state[1] : 0.0f;
+    for (int w = 1; w < W; ++w) {
+        b1p[w] = b1p[w - 1] * b1;
+        b2p[w] = b2p[w - 1] * b2;
+    }
+    cpu_ps_job jobs[256];
+    pthread_t tid[256];
+    for (int p = 0; p < parts; ++p) {
+        cpu_ps_job j = { var, m, v, slots, scratch, stride, n, worker_grad,
+                         worker_param, W, opt_adam, mode, p, parts,
+                         lr, b1, b2, eps, b1p, b2p };
+        jobs[p] = j;
+    }
+    for (int p = 1; p < parts; ++p)
+        if (pthread_create(&tid[p], NULL, cpu_ps_part, &jobs[p]) != 0)
+            return -3;
+    cpu_ps_part(&jobs[0]);
+    for (int p = 1; p < parts; ++p)
+        pthread_join(tid[p], NULL);
+    int applies = (mode == PSX_ORACLE_ASYNC_ORDERED) ? W : 1;
+    if (opt_adam) {
+        for (int k = 0; k < applies; ++k) {
+            state[0] = state[0] * b1;
+            state[1] = state[1] * b2;
+        }
+    }
+    *step += applies;
+    return parts;
+}
