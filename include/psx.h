@@ -1,0 +1,189 @@
+/*
+ * psx.h -- C ABI of libpsx.so: the B200 parameter-server data plane that stands
+ * in for what douban/tfmesos reaches through tf.train.Server.
+ *
+ * The reference defines no FFI of its own for this path: it hands the process to
+ * TensorFlow's distributed runtime at tfmesos/server.py:51-66 and the per-step
+ * work happens inside TF:
+ *
+ *   PULL   Variable -> _Send/_Recv, one RecvTensor per variable
+ *          (triggered at examples/mnist/mnist.py:71, mnist_replica.py:204,
+ *           matrix_factorization.py:45-49)
+ *   PUSH   gradient _Send/_Recv worker -> ps            (same call sites)
+ *   APPLY  ApplyGradientDescent / ApplyAdam on the PS    (mnist.py:55,
+ *          mnist_replica.py:147-157, matrix_factorization.py:39-41)
+ *
+ * Each entry point below names the reference interface it replaces.  All
+ * functions use C linkage, plain pointers and sizes; no C++ exception crosses
+ * the boundary and nothing calls exit().  Return value: 0 on success, a negative
+ * PSX_E* code otherwise, with a thread-local message behind psx_last_error()
+ * (the Python side raises RuntimeError(msg), the reference's error style at
+ * tfmesos/scheduler.py:398).  Device pointers are raw CUDA device addresses
+ * (torch.Tensor.data_ptr()); streams are cudaStream_t passed as void*
+ * (torch.cuda.current_stream().cuda_stream); 0 = the legacy default stream.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with PSX_ECUDA.
+ */
+#ifndef PSX_H_
+#define PSX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSX_ABI_VERSION 3
+
+/* error codes */
+#define PSX_OK 0
+#define PSX_EINVAL (-1)   /* bad argument / unknown id                       */
+#define PSX_ECUDA (-2)    /* CUDA runtime or driver error (message has it)    */
+#define PSX_ENOMEM (-3)
+#define PSX_ESTATE (-4)   /* call not valid in the object's current state     */
+#define PSX_EABI (-5)     /* handle blob from another ABI version             */
+
+/* optimizers (reference: mnist.py:55 / mnist_replica.py:147) */
+#define PSX_OPT_SGD 0
+#define PSX_OPT_ADAM 1
+
+/* update disciplines */
+#define PSX_MODE_ASYNC_ORDERED 0 /* each slot applied on its own, slot order  */
+#define PSX_MODE_SUM 1           /* ((g0+g1)+g2)+... then one apply           */
+#define PSX_MODE_SYNC_MEAN 2     /* sum / (float)count, one apply             */
+                                 /* (SyncReplicasOptimizer, mnist_replica.py:148-154) */
+
+/* element types on the wire / in caller buffers */
+#define PSX_F32 0
+#define PSX_BF16 1
+
+/* psx_set_values / psx_get_values selector */
+#define PSX_VAR 0
+#define PSX_M 1
+#define PSX_V 2
+#define PSX_SLOT0 16 /* PSX_SLOT0 + s selects gradient slot s (as f32)      */
+
+#define PSX_MAX_SLOTS 16
+#define PSX_HANDLE_BYTES 128 /* opaque blob shipped over the rendez-vous socket
+                                (tfmesos/utils.py:6-15 framing)              */
+
+int psx_abi_version(void);
+const char *psx_last_error(void);
+
+/* Number of CUDA devices visible; 0 with PSX_ECUDA when there is none. */
+int psx_device_count(int *out_n);
+
+/* Bind the calling process to a device before anything else: creates the
+ * primary context, resolves the stream-memop driver entry points.
+ * Replaces: tf.train.Server(server_def) start-up, tfmesos/server.py:52-61. */
+int psx_init(int device_ordinal);
+
+/* Let `device` read/write memory that lives on `peer` (idempotent). */
+int psx_enable_peer(int device, int peer);
+
+/* ------------------------------------------------------------------ PS side */
+
+/* Allocate one PS shard in HBM on `device`: a flat f32 bucket `var[nelem]`
+ * (+ Adam `m`,`v`, stored beta powers, global_step) and `n_slots` gradient
+ * landing slots of `wire_dtype`, plus the flag words the kernels synchronise
+ * on.  hyper = {lr, beta1, beta2, epsilon}.
+ * Replaces: variables + slot variables created on /job:ps/task:k by
+ * replica_device_setter (mnist.py:43-46, mnist_replica.py:116-134) and
+ * tf.get_variable under tf.device (matrix_factorization.py:21-28). */
+int psx_shard_create(int device, uint64_t nelem, int opt, const float *hyper,
+                     int n_slots, int wire_dtype, uint64_t *out_id);
+int psx_shard_destroy(uint64_t id);
+/* Blob a worker passes to psx_shard_open (CUDA-IPC inside). */
+int psx_shard_export(uint64_t id, void *out_handle);
+int psx_shard_set_hyper(uint64_t id, const float *hyper);
+
+/* Synchronous host copies for init / tests / checkpoint.
+ * Replaces: init_op (mnist.py:59, mnist_replica.py:164), Variable.eval()
+ * (matrix_factorization.py:49). */
+int psx_set_values(uint64_t id, int which, const float *host, uint64_t off, uint64_t n);
+int psx_get_values(uint64_t id, int which, float *host, uint64_t off, uint64_t n);
+/* stored Adam powers, global_step, number of completed apply rounds */
+int psx_get_state(uint64_t id, float *b1p, float *b2p, int64_t *step, uint32_t *apply_seq);
+int psx_set_state(uint64_t id, float b1p, float b2p, int64_t step);
+
+/* Fused reduce(slots) + SGD/Adam + beta-power / global_step update over the
+ * whole shard.  If wait_seq != 0 the stream first waits (cuStreamWaitValue32,
+ * no SM is held) until every slot in [first_slot, first_slot+count) has been
+ * pushed with seq >= wait_seq.  On completion the shard's apply_seq is
+ * incremented and mirrored into every registered client.
+ * Replaces: ApplyGradientDescent / ApplyAdam + AdamOptimizer._finish +
+ * global_step assign_add on the PS (mnist.py:55; mnist_replica.py:147,156-157),
+ * and SyncReplicasOptimizer's aggregation (mnist_replica.py:148-154). */
+int psx_apply(uint64_t id, int mode, int first_slot, int count, uint32_t wait_seq,
+              void *stream);
+
+/* ------------------------------------------------------------- worker side */
+
+/* Map a PS shard into this process for use from `device` as gradient slot
+ * `slot`.  Same-process handles are mapped directly, others through CUDA IPC.
+ * Replaces: tf.Session(target) attaching to the PS devices (mnist.py:65,
+ * mnist_replica.py:183, matrix_factorization.py:68). */
+int psx_shard_open(const void *handle, int device, int slot, uint64_t *out_id);
+int psx_shard_close(uint64_t id);
+/* Blob for psx_shard_register_client: lets the PS mirror apply_seq into this
+ * worker's HBM so the worker's pull waits on local memory. */
+int psx_client_export(uint64_t client_id, void *out_handle);
+int psx_shard_register_client(uint64_t shard_id, int slot, const void *client_handle);
+
+/* PUSH: copy n gradient elements grad_dev[0..n) into elements [off, off+n) of
+ * this client's slot in the PS shard's HBM (vectorised stores, straight over
+ * NVLink when the shard is on another GPU), then publish `seq` in the slot's
+ * flag word (st.release.sys) unless seq == 0.  src_dtype: type of grad_dev.
+ * Replaces: gradient _Send/_Recv worker->ps, one RecvTensor per variable. */
+int psx_push(uint64_t client_id, const void *grad_dev, uint64_t off, uint64_t n,
+             int src_dtype, uint32_t seq, void *stream);
+
+/* PULL: copy var[off, off+n) from the PS shard into param_dev[0..n), cast to
+ * out_dtype.  If wait_seq != 0 the stream first waits until the shard has
+ * completed apply round wait_seq.
+ * Replaces: Variable read _Send/_Recv ps->worker, one RecvTensor per variable. */
+int psx_pull(uint64_t client_id, void *param_dev, uint64_t off, uint64_t n,
+             int out_dtype, uint32_t wait_seq, void *stream);
+
+/* ---------------------------------------------- one-shot fused round (sync) */
+
+/* Exportable device buffers (worker gradient / parameter staging the PS-side
+ * fused kernel reads and writes over NVLink). */
+int psx_buffer_create(int device, uint64_t nbytes, uint64_t *out_id, void **out_dev_ptr);
+int psx_buffer_export(uint64_t id, void *out_handle);
+int psx_buffer_destroy(uint64_t id);
+
+/* Bind worker `slot`'s gradient and parameter buffers (f32, elements
+ * [elem_off, elem_off + shard nelem) of each) to a shard for psx_round. */
+int psx_round_bind(uint64_t shard_id, int slot, const void *grad_buf_handle,
+                   const void *param_buf_handle, uint64_t elem_off);
+
+/* Worker: "my bound gradient buffer holds round `seq`" (release store into the
+ * shard's slot flag).  Worker: wait until apply round `seq` is done. */
+int psx_signal(uint64_t client_id, uint32_t seq, void *stream);
+int psx_wait_applied(uint64_t client_id, uint32_t seq, void *stream);
+
+/* ONE kernel on the PS GPU: gather the bound gradients straight from the
+ * workers' HBM (peer loads), reduce in registers in slot order, apply
+ * SGD/Adam to var/m/v in place, and scatter the new parameters into every
+ * bound parameter buffer (peer stores) -- push + sum + apply + pull with no
+ * staging copy.  Waits like psx_apply. */
+int psx_round(uint64_t shard_id, int mode, int first_slot, int count, uint32_t wait_seq,
+              void *stream);
+
+/* ------------------------------------------------------------ diagnostics */
+
+/* Kernel launches issued by this library in this process since load. */
+uint64_t psx_launch_count(void);
+/* Raw device pointers (for zero-copy use by a co-resident worker and for
+ * tests): which = PSX_VAR/PSX_M/PSX_V/PSX_SLOT0+s. */
+int psx_shard_ptr(uint64_t id, int which, void **out_dev_ptr);
+/* Plain device->device copy through the push kernel (bandwidth probes). */
+int psx_copy(int device, void *dst, const void *src, uint64_t nbytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSX_H_ */

@@ -300,12 +300,18 @@ def run_cluster_def(make_scheduler, install_driver=None, D=None):
             Drv.D = addict.Dict
         else:
             Drv.D = D
+        mod, orig_driver = None, None
         if install_driver is None:
             mod = sys.modules[type(sched).__module__]
+            orig_driver = mod.MesosSchedulerDriver
             mod.MesosSchedulerDriver = Drv
         else:
             install_driver(sched, Drv)
-        sched.start()
+        try:
+            sched.start()
+        finally:
+            if mod is not None:
+                mod.MesosSchedulerDriver = orig_driver
         drv = holder["drv"]
         for t in drv.threads:
             t.join(30)

@@ -1,0 +1,916 @@
+// psx.cu -- host runtime + C ABI (include/psx.h) of the B200 parameter-server
+// data plane.  One process per GPU is the normal deployment (the process that
+// replaces tf.train.Server at tfmesos/server.py:51-66); several devices in one
+// process also work (every object remembers its device).
+//
+// Memory model
+//   shard   = ONE cudaMalloc on the PS GPU:  [header 4 KiB | var | m | v | slots]
+//             exported with CUDA IPC; workers map the whole thing and write
+//             their gradient slot + its flag word directly over NVLink.
+//   client  = a worker's attachment to a shard: mapped pointers + a 256 B block
+//             in the WORKER's HBM (push ticket, mirror of apply_seq).
+//   buffer  = exportable worker staging (gradients / parameters) for psx_round.
+// Waiting never holds an SM: consumers wait with cuStreamWaitValue32 on a flag
+// in their OWN HBM that the producer's kernel release-stores remotely.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "psx.h"
+#include "psx_kernels.cuh"
+
+using namespace psx;
+
+namespace {
+
+// ------------------------------------------------------------------ errors --
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                   \
+    do {                                                                               \
+        cudaError_t e_ = (expr);                                                       \
+        if (e_ != cudaSuccess)                                                         \
+            return fail(PSX_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                           \
+    } while (0)
+
+// Entry points run on the object's device and put the caller's device back
+// (torch tracks the thread's current device through the same driver state).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int device)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define PSX_DEVICE(dev)                                                                  \
+    DeviceGuard guard_(dev);                                                             \
+    if (guard_.err != cudaSuccess)                                                       \
+        return fail(PSX_ECUDA, "selecting device %d: %s", (int)(dev), cudaGetErrorString(guard_.err))
+
+// ------------------------------------------------------------ driver memops --
+typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+WaitValue32Fn g_wait32 = nullptr;
+std::once_flag g_wait_once;
+
+int resolve_memops()
+{
+    std::call_once(g_wait_once, [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) ==
+                cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            g_wait32 = (WaitValue32Fn)fn;
+    });
+    if (!g_wait32) return fail(PSX_ECUDA, "cuStreamWaitValue32 not available from the driver");
+    return PSX_OK;
+}
+
+int stream_wait_geq(void *stream, unsigned int *flag, uint32_t value)
+{
+    int rc = resolve_memops();
+    if (rc) return rc;
+    CUresult r = g_wait32((CUstream)stream, (CUdeviceptr)(uintptr_t)flag, value,
+                          CU_STREAM_WAIT_VALUE_GEQ);
+    if (r != CUDA_SUCCESS) return fail(PSX_ECUDA, "cuStreamWaitValue32 failed: CUresult %d", (int)r);
+    return PSX_OK;
+}
+
+// ---------------------------------------------------------------- objects ---
+constexpr uint32_t kMagic = 0x50535831u;  // "PSX1"
+constexpr size_t kHeaderBytes = 4096;
+constexpr uint64_t kPadElems = 1024;      // every region starts 4 KiB aligned
+
+enum Kind : uint32_t { KIND_SHARD = 1, KIND_CLIENT = 2, KIND_BUFFER = 3 };
+
+struct HandleBlob {           // PSX_HANDLE_BYTES, shipped between processes
+    uint32_t magic, abi, kind;
+    int32_t device;
+    uint64_t pid, local_id, nelem, nelem_pad;
+    int32_t opt, n_slots, wire;
+    uint32_t pad;
+    cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(HandleBlob) == PSX_HANDLE_BYTES, "handle blob size");
+
+struct Layout {
+    uint64_t nelem = 0, nelem_pad = 0;
+    int opt = 0, n_slots = 0, wire = 0;
+    size_t wire_bytes() const { return wire == PSX_BF16 ? 2 : 4; }
+    size_t off_var() const { return kHeaderBytes; }
+    size_t off_m() const { return off_var() + nelem_pad * 4; }
+    size_t off_v() const { return off_m() + (opt == PSX_OPT_ADAM ? nelem_pad * 4 : 0); }
+    size_t off_slots() const { return off_v() + (opt == PSX_OPT_ADAM ? nelem_pad * 4 : 0); }
+    size_t total() const { return off_slots() + (size_t)n_slots * nelem_pad * wire_bytes(); }
+};
+
+struct Mapped {               // a peer allocation opened in this process
+    char *base = nullptr;
+    bool ipc = false;         // needs cudaIpcCloseMemHandle
+    int device = 0;
+};
+
+struct Bound {
+    Mapped grad, param;
+    uint64_t elem_off = 0;
+    bool valid = false;
+};
+
+struct Shard {
+    int device = 0;
+    Layout lay;
+    char *base = nullptr;
+    int sm_count = 148;
+    Mapped client_map[PSX_MAX_SLOTS];
+    unsigned int *mirror[PSX_MAX_SLOTS] = {};
+    Bound bound[PSX_MAX_SLOTS];
+    ShardHeader *hdr() const { return (ShardHeader *)base; }
+    float *var() const { return (float *)(base + lay.off_var()); }
+    float *m() const { return (float *)(base + lay.off_m()); }
+    float *v() const { return (float *)(base + lay.off_v()); }
+    char *slot(int s) const { return base + lay.off_slots() + (size_t)s * lay.nelem_pad * lay.wire_bytes(); }
+};
+
+struct Client {
+    int device = 0;           // the worker's device
+    int slot = 0;
+    Layout lay;
+    Mapped shard;             // the PS allocation as seen from here
+    ClientBlock *block = nullptr;  // in this device's HBM
+    int sm_count = 148;
+    ShardHeader *hdr() const { return (ShardHeader *)shard.base; }
+    float *var() const { return (float *)(shard.base + lay.off_var()); }
+    char *my_slot() const { return shard.base + lay.off_slots() + (size_t)slot * lay.nelem_pad * lay.wire_bytes(); }
+};
+
+struct Buffer {
+    int device = 0;
+    uint64_t nbytes = 0;
+    char *base = nullptr;
+};
+
+std::mutex g_mu;
+std::unordered_map<uint64_t, Shard *> g_shards;
+std::unordered_map<uint64_t, Client *> g_clients;
+std::unordered_map<uint64_t, Buffer *> g_buffers;
+std::atomic<uint64_t> g_next_id{1};
+std::atomic<uint64_t> g_launches{0};
+
+template <typename T> T *find(std::unordered_map<uint64_t, T *> &m, uint64_t id)
+{
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = m.find(id);
+    return it == m.end() ? nullptr : it->second;
+}
+
+int sm_count_of(int device)
+{
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+    return n > 0 ? n : 148;
+}
+
+int open_blob(const HandleBlob &b, int device, Mapped *out)
+{
+    out->device = b.device;
+    if (b.pid == (uint64_t)getpid()) {  // same process: direct pointer
+        std::lock_guard<std::mutex> lk(g_mu);
+        char *base = nullptr;
+        if (b.kind == KIND_SHARD) {
+            auto it = g_shards.find(b.local_id);
+            if (it != g_shards.end()) base = it->second->base;
+        } else if (b.kind == KIND_CLIENT) {
+            auto it = g_clients.find(b.local_id);
+            if (it != g_clients.end()) base = (char *)it->second->block;
+        } else if (b.kind == KIND_BUFFER) {
+            auto it = g_buffers.find(b.local_id);
+            if (it != g_buffers.end()) base = it->second->base;
+        }
+        if (!base) return fail(PSX_EINVAL, "handle refers to an object this process no longer has");
+        out->base = base;
+        out->ipc = false;
+        return PSX_OK;
+    }
+    PSX_DEVICE(device);
+    void *p = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(&p, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+    out->base = (char *)p;
+    out->ipc = true;
+    return PSX_OK;
+}
+
+void close_mapped(Mapped &m)
+{
+    if (m.ipc && m.base) cudaIpcCloseMemHandle(m.base);
+    m.base = nullptr;
+    m.ipc = false;
+}
+
+int check_blob(const void *handle, uint32_t kind, HandleBlob *out)
+{
+    if (!handle) return fail(PSX_EINVAL, "null handle");
+    memcpy(out, handle, sizeof(HandleBlob));
+    if (out->magic != kMagic) return fail(PSX_EINVAL, "not a psx handle");
+    if (out->abi != PSX_ABI_VERSION)
+        return fail(PSX_EABI, "handle from ABI %u, library is ABI %d", out->abi, PSX_ABI_VERSION);
+    if (out->kind != kind) return fail(PSX_EINVAL, "handle kind %u, expected %u", out->kind, kind);
+    return PSX_OK;
+}
+
+int enable_peer(int device, int peer)
+{
+    if (device == peer) return PSX_OK;
+    int can = 0;
+    CU_TRY(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) return fail(PSX_ECUDA, "device %d cannot access peer %d", device, peer);
+    PSX_DEVICE(device);
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return PSX_OK;
+    }
+    if (e != cudaSuccess) return fail(PSX_ECUDA, "cudaDeviceEnablePeerAccess(%d->%d): %s", device, peer, cudaGetErrorString(e));
+    return PSX_OK;
+}
+
+inline int grid_for(size_t work_items, int threads, int sm_count, int ctas_per_sm)
+{
+    size_t need = (work_items + threads - 1) / threads;
+    size_t cap = (size_t)sm_count * ctas_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+#define LAUNCH_CHECK()                                                              \
+    do {                                                                            \
+        cudaError_t e_ = cudaGetLastError();                                        \
+        if (e_ != cudaSuccess)                                                      \
+            return fail(PSX_ECUDA, "kernel launch failed: %s (%s:%d)",              \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                         \
+    } while (0)
+
+// dst/src element types resolved at run time -> the four k_copy instances
+int launch_copy(void *dst, int dst_t, const void *src, int src_t, uint64_t n, int sm_count,
+                unsigned int *ticket, unsigned int *flag, uint32_t seq, cudaStream_t st)
+{
+    if (n == 0 && flag == nullptr) return PSX_OK;
+    const size_t sb = src_t == PSX_BF16 ? 2 : 4, db = dst_t == PSX_BF16 ? 2 : 4;
+    // 4-element vectors: f32 needs 16 B alignment, bf16 8 B
+    const int vec_ok = (((uintptr_t)src % (4 * sb)) == 0) && (((uintptr_t)dst % (4 * db)) == 0);
+    const size_t items = vec_ok ? ((n >> 2) + kCopyUnroll - 1) / kCopyUnroll : n;
+    const int grid = grid_for(items ? items : 1, kCopyThreads, sm_count, 8);
+#define PSX_COPY(S, D)                                                                        \
+    k_copy<S, D><<<grid, kCopyThreads, 0, st>>>((D *)dst, (const S *)src, (size_t)n, vec_ok, \
+                                                 ticket, flag, seq)
+    if (src_t == PSX_F32 && dst_t == PSX_F32) PSX_COPY(float, float);
+    else if (src_t == PSX_F32 && dst_t == PSX_BF16) PSX_COPY(float, __nv_bfloat16);
+    else if (src_t == PSX_BF16 && dst_t == PSX_F32) PSX_COPY(__nv_bfloat16, float);
+    else if (src_t == PSX_BF16 && dst_t == PSX_BF16) PSX_COPY(__nv_bfloat16, __nv_bfloat16);
+    else return fail(PSX_EINVAL, "unknown dtype %d/%d", src_t, dst_t);
+#undef PSX_COPY
+    LAUNCH_CHECK();
+    return PSX_OK;
+}
+
+template <int OPT, int MODE, bool SCATTER, typename SRC>
+void launch_apply_t(Shard *s, SRC src, int count, const PeerSet &peers, cudaStream_t st)
+{
+    const size_t n4 = s->lay.nelem_pad / 4;
+    const int grid = grid_for(n4, kApplyThreads, s->sm_count, 3);
+    k_apply<OPT, MODE, SCATTER, SRC><<<grid, kApplyThreads, 0, st>>>(
+        s->hdr(), (float4 *)s->var(), (float4 *)s->m(), (float4 *)s->v(), src, count, n4, peers);
+}
+
+template <bool SCATTER, typename SRC>
+int launch_apply(Shard *s, int mode, SRC src, int count, const PeerSet &peers, cudaStream_t st)
+{
+#define PSX_AP(O, M) launch_apply_t<O, M, SCATTER, SRC>(s, src, count, peers, st)
+    const int opt = s->lay.opt;
+    if (opt == PSX_OPT_SGD && mode == PSX_MODE_ASYNC_ORDERED) PSX_AP(PSX_OPT_SGD, PSX_MODE_ASYNC_ORDERED);
+    else if (opt == PSX_OPT_SGD && mode == PSX_MODE_SUM) PSX_AP(PSX_OPT_SGD, PSX_MODE_SUM);
+    else if (opt == PSX_OPT_SGD && mode == PSX_MODE_SYNC_MEAN) PSX_AP(PSX_OPT_SGD, PSX_MODE_SYNC_MEAN);
+    else if (opt == PSX_OPT_ADAM && mode == PSX_MODE_ASYNC_ORDERED) PSX_AP(PSX_OPT_ADAM, PSX_MODE_ASYNC_ORDERED);
+    else if (opt == PSX_OPT_ADAM && mode == PSX_MODE_SUM) PSX_AP(PSX_OPT_ADAM, PSX_MODE_SUM);
+    else if (opt == PSX_OPT_ADAM && mode == PSX_MODE_SYNC_MEAN) PSX_AP(PSX_OPT_ADAM, PSX_MODE_SYNC_MEAN);
+    else return fail(PSX_EINVAL, "unknown optimizer/mode %d/%d", opt, mode);
+#undef PSX_AP
+    LAUNCH_CHECK();
+    return PSX_OK;
+}
+
+void fill_mirrors(Shard *s, PeerSet *p)
+{
+    p->n_mirror = 0;
+    p->n_param = 0;
+    for (int c = 0; c < PSX_MAX_SLOTS; ++c)
+        if (s->mirror[c]) p->mirror[p->n_mirror++] = s->mirror[c];
+}
+
+int wait_slots(Shard *s, int first, int count, uint32_t wait_seq, void *stream)
+{
+    if (wait_seq == 0) return PSX_OK;
+    for (int k = 0; k < count; ++k) {
+        int rc = stream_wait_geq(stream, &s->hdr()->slot_seq[first + k], wait_seq);
+        if (rc) return rc;
+    }
+    return PSX_OK;
+}
+
+int check_range(int first, int count, int n_slots)
+{
+    if (count < 1 || first < 0 || first + count > n_slots || count > PSX_MAX_SLOTS)
+        return fail(PSX_EINVAL, "slot range [%d, %d) outside the shard's %d slots", first,
+                    first + count, n_slots);
+    return PSX_OK;
+}
+
+}  // namespace
+
+// =============================================================== C ABI =======
+extern "C" {
+
+int psx_abi_version(void) { return PSX_ABI_VERSION; }
+
+const char *psx_last_error(void) { return g_err; }
+
+uint64_t psx_launch_count(void) { return g_launches.load(); }
+
+int psx_device_count(int *out_n)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (out_n) *out_n = (e == cudaSuccess) ? n : 0;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PSX_ECUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    if (n == 0) return fail(PSX_ECUDA, "no CUDA device visible");
+    return PSX_OK;
+}
+
+int psx_init(int device)
+{
+    int n = 0;
+    int rc = psx_device_count(&n);
+    if (rc) return rc;
+    if (device < 0 || device >= n) return fail(PSX_EINVAL, "device %d out of range [0,%d)", device, n);
+    CU_TRY(cudaSetDevice(device));  // sticks: this is the process's device from now on
+    CU_TRY(cudaFree(0));            // force the primary context
+    return resolve_memops();
+}
+
+int psx_enable_peer(int device, int peer) { return enable_peer(device, peer); }
+
+// ------------------------------------------------------------------ PS side --
+int psx_shard_create(int device, uint64_t nelem, int opt, const float *hyper, int n_slots,
+                     int wire_dtype, uint64_t *out_id)
+{
+    if (!out_id || !hyper) return fail(PSX_EINVAL, "null argument");
+    if (nelem == 0) return fail(PSX_EINVAL, "empty shard");
+    if (opt != PSX_OPT_SGD && opt != PSX_OPT_ADAM) return fail(PSX_EINVAL, "unknown optimizer %d", opt);
+    if (n_slots < 0 || n_slots > PSX_MAX_SLOTS) return fail(PSX_EINVAL, "n_slots %d not in [0,%d]", n_slots, PSX_MAX_SLOTS);
+    if (wire_dtype != PSX_F32 && wire_dtype != PSX_BF16) return fail(PSX_EINVAL, "unknown wire dtype %d", wire_dtype);
+    PSX_DEVICE(device);
+    Shard *s = new Shard();
+    s->device = device;
+    s->lay.nelem = nelem;
+    s->lay.nelem_pad = (nelem + kPadElems - 1) / kPadElems * kPadElems;
+    s->lay.opt = opt;
+    s->lay.n_slots = n_slots;
+    s->lay.wire = wire_dtype;
+    s->sm_count = sm_count_of(device);
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, s->lay.total());
+    if (e != cudaSuccess) {
+        size_t total = s->lay.total();
+        delete s;
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? PSX_ENOMEM : PSX_ECUDA,
+                    "cudaMalloc(%zu bytes) for shard: %s", total, cudaGetErrorString(e));
+    }
+    s->base = (char *)p;
+    e = cudaMemset(p, 0, s->lay.total());
+    ShardHeader h;
+    memset(&h, 0, sizeof(h));
+    h.magic = kMagic;
+    h.abi = PSX_ABI_VERSION;
+    h.lr = hyper[0];
+    h.b1 = hyper[1];
+    h.b2 = hyper[2];
+    h.eps = hyper[3];
+    h.b1p = hyper[1];  // powers start at beta (AdamOptimizer._create_slots)
+    h.b2p = hyper[2];
+    if (e == cudaSuccess) e = cudaMemcpy(p, &h, sizeof(h), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        delete s;
+        return fail(PSX_ECUDA, "initialising shard: %s", cudaGetErrorString(e));
+    }
+    uint64_t id = g_next_id.fetch_add(1);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_shards[id] = s;
+    }
+    *out_id = id;
+    return PSX_OK;
+}
+
+int psx_shard_destroy(uint64_t id)
+{
+    Shard *s = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_shards.find(id);
+        if (it == g_shards.end()) return fail(PSX_EINVAL, "unknown shard id %llu", (unsigned long long)id);
+        s = it->second;
+        g_shards.erase(it);
+    }
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    for (int c = 0; c < PSX_MAX_SLOTS; ++c) {
+        close_mapped(s->client_map[c]);
+        close_mapped(s->bound[c].grad);
+        close_mapped(s->bound[c].param);
+    }
+    cudaFree(s->base);
+    delete s;
+    return PSX_OK;
+}
+
+int psx_shard_export(uint64_t id, void *out_handle)
+{
+    Shard *s = find(g_shards, id);
+    if (!s || !out_handle) return fail(PSX_EINVAL, "unknown shard id or null handle");
+    HandleBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = kMagic;
+    b.abi = PSX_ABI_VERSION;
+    b.kind = KIND_SHARD;
+    b.device = s->device;
+    b.pid = (uint64_t)getpid();
+    b.local_id = id;
+    b.nelem = s->lay.nelem;
+    b.nelem_pad = s->lay.nelem_pad;
+    b.opt = s->lay.opt;
+    b.n_slots = s->lay.n_slots;
+    b.wire = s->lay.wire;
+    PSX_DEVICE(s->device);
+    CU_TRY(cudaIpcGetMemHandle(&b.ipc, s->base));
+    memcpy(out_handle, &b, sizeof(b));
+    return PSX_OK;
+}
+
+int psx_shard_set_hyper(uint64_t id, const float *hyper)
+{
+    Shard *s = find(g_shards, id);
+    if (!s || !hyper) return fail(PSX_EINVAL, "unknown shard id or null hyper");
+    PSX_DEVICE(s->device);
+    CU_TRY(cudaMemcpy(&s->hdr()->lr, hyper, 4 * sizeof(float), cudaMemcpyHostToDevice));
+    return PSX_OK;
+}
+
+static int region_of(Shard *s, int which, char **base, int *dtype)
+{
+    *dtype = PSX_F32;
+    if (which == PSX_VAR) *base = (char *)s->var();
+    else if (which == PSX_M && s->lay.opt == PSX_OPT_ADAM) *base = (char *)s->m();
+    else if (which == PSX_V && s->lay.opt == PSX_OPT_ADAM) *base = (char *)s->v();
+    else if (which >= PSX_SLOT0 && which < PSX_SLOT0 + s->lay.n_slots) {
+        *base = s->slot(which - PSX_SLOT0);
+        *dtype = s->lay.wire;
+    } else
+        return fail(PSX_EINVAL, "shard has no region %d", which);
+    return PSX_OK;
+}
+
+int psx_set_values(uint64_t id, int which, const float *host, uint64_t off, uint64_t n)
+{
+    Shard *s = find(g_shards, id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    if (off + n > s->lay.nelem) return fail(PSX_EINVAL, "range [%llu,+%llu) outside shard of %llu", (unsigned long long)off, (unsigned long long)n, (unsigned long long)s->lay.nelem);
+    char *base;
+    int dt;
+    int rc = region_of(s, which, &base, &dt);
+    if (rc) return rc;
+    if (n == 0) return PSX_OK;
+    PSX_DEVICE(s->device);
+    if (dt == PSX_F32) {
+        CU_TRY(cudaMemcpy(base + off * 4, host, n * 4, cudaMemcpyHostToDevice));
+    } else {  // stage f32 on the device, cast with the push kernel
+        void *tmp = nullptr;
+        CU_TRY(cudaMalloc(&tmp, n * 4));
+        cudaError_t e = cudaMemcpy(tmp, host, n * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            rc = launch_copy(base + off * 2, PSX_BF16, tmp, PSX_F32, n, s->sm_count, nullptr, nullptr, 0, 0);
+            e = cudaDeviceSynchronize();
+        }
+        cudaFree(tmp);
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(PSX_ECUDA, "set_values(bf16): %s", cudaGetErrorString(e));
+    }
+    return PSX_OK;
+}
+
+int psx_get_values(uint64_t id, int which, float *host, uint64_t off, uint64_t n)
+{
+    Shard *s = find(g_shards, id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    if (off + n > s->lay.nelem) return fail(PSX_EINVAL, "range outside shard");
+    char *base;
+    int dt;
+    int rc = region_of(s, which, &base, &dt);
+    if (rc) return rc;
+    if (n == 0) return PSX_OK;
+    PSX_DEVICE(s->device);
+    CU_TRY(cudaDeviceSynchronize());
+    if (dt == PSX_F32) {
+        CU_TRY(cudaMemcpy(host, base + off * 4, n * 4, cudaMemcpyDeviceToHost));
+    } else {
+        void *tmp = nullptr;
+        CU_TRY(cudaMalloc(&tmp, n * 4));
+        rc = launch_copy(tmp, PSX_F32, base + off * 2, PSX_BF16, n, s->sm_count, nullptr, nullptr, 0, 0);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess) e = cudaMemcpy(host, tmp, n * 4, cudaMemcpyDeviceToHost);
+        cudaFree(tmp);
+        if (rc) return rc;
+        if (e != cudaSuccess) return fail(PSX_ECUDA, "get_values(bf16): %s", cudaGetErrorString(e));
+    }
+    return PSX_OK;
+}
+
+int psx_get_state(uint64_t id, float *b1p, float *b2p, int64_t *step, uint32_t *apply_seq)
+{
+    Shard *s = find(g_shards, id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    PSX_DEVICE(s->device);
+    CU_TRY(cudaDeviceSynchronize());
+    ShardHeader h;
+    CU_TRY(cudaMemcpy(&h, s->base, sizeof(h), cudaMemcpyDeviceToHost));
+    if (b1p) *b1p = h.b1p;
+    if (b2p) *b2p = h.b2p;
+    if (step) *step = h.step;
+    if (apply_seq) *apply_seq = h.apply_seq;
+    return PSX_OK;
+}
+
+int psx_set_state(uint64_t id, float b1p, float b2p, int64_t step)
+{
+    Shard *s = find(g_shards, id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    PSX_DEVICE(s->device);
+    CU_TRY(cudaDeviceSynchronize());
+    ShardHeader h;
+    CU_TRY(cudaMemcpy(&h, s->base, sizeof(h), cudaMemcpyDeviceToHost));
+    h.b1p = b1p;
+    h.b2p = b2p;
+    h.step = step;
+    CU_TRY(cudaMemcpy(s->base, &h, offsetof(ShardHeader, ticket), cudaMemcpyHostToDevice));
+    return PSX_OK;
+}
+
+int psx_shard_ptr(uint64_t id, int which, void **out_dev_ptr)
+{
+    Shard *s = find(g_shards, id);
+    if (!s || !out_dev_ptr) return fail(PSX_EINVAL, "unknown shard id or null out pointer");
+    char *base;
+    int dt;
+    int rc = region_of(s, which, &base, &dt);
+    if (rc) return rc;
+    *out_dev_ptr = base;
+    return PSX_OK;
+}
+
+int psx_apply(uint64_t id, int mode, int first_slot, int count, uint32_t wait_seq, void *stream)
+{
+    Shard *s = find(g_shards, id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    int rc = check_range(first_slot, count, s->lay.n_slots);
+    if (rc) return rc;
+    PSX_DEVICE(s->device);
+    rc = wait_slots(s, first_slot, count, wait_seq, stream);
+    if (rc) return rc;
+    PeerSet peers;
+    memset(&peers, 0, sizeof(peers));
+    fill_mirrors(s, &peers);
+    if (s->lay.wire == PSX_F32) {
+        SlotSrc<float> src{(const float *)s->slot(0), (size_t)s->lay.nelem_pad, first_slot};
+        return launch_apply<false>(s, mode, src, count, peers, (cudaStream_t)stream);
+    }
+    SlotSrc<__nv_bfloat16> src{(const __nv_bfloat16 *)s->slot(0), (size_t)s->lay.nelem_pad, first_slot};
+    return launch_apply<false>(s, mode, src, count, peers, (cudaStream_t)stream);
+}
+
+int psx_shard_register_client(uint64_t shard_id, int slot, const void *client_handle)
+{
+    Shard *s = find(g_shards, shard_id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    if (slot < 0 || slot >= PSX_MAX_SLOTS) return fail(PSX_EINVAL, "slot %d out of range", slot);
+    HandleBlob b;
+    int rc = check_blob(client_handle, KIND_CLIENT, &b);
+    if (rc) return rc;
+    if (s->mirror[slot]) {
+        close_mapped(s->client_map[slot]);
+        s->mirror[slot] = nullptr;
+    }
+    rc = enable_peer(s->device, b.device);
+    if (rc) return rc;
+    rc = open_blob(b, s->device, &s->client_map[slot]);
+    if (rc) return rc;
+    s->mirror[slot] = &((ClientBlock *)s->client_map[slot].base)->applied;
+    return PSX_OK;
+}
+
+// -------------------------------------------------------------- worker side --
+int psx_shard_open(const void *handle, int device, int slot, uint64_t *out_id)
+{
+    if (!out_id) return fail(PSX_EINVAL, "null out id");
+    HandleBlob b;
+    int rc = check_blob(handle, KIND_SHARD, &b);
+    if (rc) return rc;
+    if (slot < 0 || (b.n_slots > 0 && slot >= b.n_slots))
+        return fail(PSX_EINVAL, "slot %d outside the shard's %d slots", slot, b.n_slots);
+    rc = enable_peer(device, b.device);
+    if (rc) return rc;
+    Client *c = new Client();
+    c->device = device;
+    c->slot = slot;
+    c->lay.nelem = b.nelem;
+    c->lay.nelem_pad = b.nelem_pad;
+    c->lay.opt = b.opt;
+    c->lay.n_slots = b.n_slots;
+    c->lay.wire = b.wire;
+    c->sm_count = sm_count_of(device);
+    rc = open_blob(b, device, &c->shard);
+    if (rc) {
+        delete c;
+        return rc;
+    }
+    DeviceGuard guard(device);
+    cudaError_t e = guard.err;
+    void *blk = nullptr;
+    if (e == cudaSuccess) e = cudaMalloc(&blk, sizeof(ClientBlock));
+    if (e == cudaSuccess) e = cudaMemset(blk, 0, sizeof(ClientBlock));
+    if (e != cudaSuccess) {
+        close_mapped(c->shard);
+        delete c;
+        return fail(PSX_ECUDA, "allocating client block: %s", cudaGetErrorString(e));
+    }
+    c->block = (ClientBlock *)blk;
+    uint64_t id = g_next_id.fetch_add(1);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_clients[id] = c;
+    }
+    *out_id = id;
+    return PSX_OK;
+}
+
+int psx_shard_close(uint64_t id)
+{
+    Client *c = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_clients.find(id);
+        if (it == g_clients.end()) return fail(PSX_EINVAL, "unknown client id");
+        c = it->second;
+        g_clients.erase(it);
+    }
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    close_mapped(c->shard);
+    cudaFree(c->block);
+    delete c;
+    return PSX_OK;
+}
+
+int psx_client_export(uint64_t client_id, void *out_handle)
+{
+    Client *c = find(g_clients, client_id);
+    if (!c || !out_handle) return fail(PSX_EINVAL, "unknown client id or null handle");
+    HandleBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = kMagic;
+    b.abi = PSX_ABI_VERSION;
+    b.kind = KIND_CLIENT;
+    b.device = c->device;
+    b.pid = (uint64_t)getpid();
+    b.local_id = client_id;
+    PSX_DEVICE(c->device);
+    CU_TRY(cudaIpcGetMemHandle(&b.ipc, c->block));
+    memcpy(out_handle, &b, sizeof(b));
+    return PSX_OK;
+}
+
+int psx_push(uint64_t client_id, const void *grad_dev, uint64_t off, uint64_t n, int src_dtype,
+             uint32_t seq, void *stream)
+{
+    Client *c = find(g_clients, client_id);
+    if (!c) return fail(PSX_EINVAL, "unknown client id");
+    if (c->lay.n_slots == 0) return fail(PSX_ESTATE, "shard was created without gradient slots");
+    if (off + n > c->lay.nelem) return fail(PSX_EINVAL, "push range [%llu,+%llu) outside shard of %llu", (unsigned long long)off, (unsigned long long)n, (unsigned long long)c->lay.nelem);
+    if (n && !grad_dev) return fail(PSX_EINVAL, "null gradient pointer");
+    PSX_DEVICE(c->device);
+    char *dst = c->my_slot() + off * c->lay.wire_bytes();
+    unsigned int *flag = seq ? &c->hdr()->slot_seq[c->slot] : nullptr;
+    return launch_copy(dst, c->lay.wire, grad_dev, src_dtype, n, c->sm_count, &c->block->ticket,
+                       flag, seq, (cudaStream_t)stream);
+}
+
+int psx_pull(uint64_t client_id, void *param_dev, uint64_t off, uint64_t n, int out_dtype,
+             uint32_t wait_seq, void *stream)
+{
+    Client *c = find(g_clients, client_id);
+    if (!c) return fail(PSX_EINVAL, "unknown client id");
+    if (off + n > c->lay.nelem) return fail(PSX_EINVAL, "pull range outside shard");
+    if (n && !param_dev) return fail(PSX_EINVAL, "null parameter pointer");
+    PSX_DEVICE(c->device);
+    if (wait_seq) {
+        int rc = stream_wait_geq(stream, &c->block->applied, wait_seq);
+        if (rc) return rc;
+    }
+    if (n == 0) return PSX_OK;
+    return launch_copy(param_dev, out_dtype, c->var() + off, PSX_F32, n, c->sm_count, nullptr,
+                       nullptr, 0, (cudaStream_t)stream);
+}
+
+int psx_signal(uint64_t client_id, uint32_t seq, void *stream)
+{
+    Client *c = find(g_clients, client_id);
+    if (!c) return fail(PSX_EINVAL, "unknown client id");
+    PSX_DEVICE(c->device);
+    k_signal<<<1, 1, 0, (cudaStream_t)stream>>>(&c->hdr()->slot_seq[c->slot], seq);
+    LAUNCH_CHECK();
+    return PSX_OK;
+}
+
+int psx_wait_applied(uint64_t client_id, uint32_t seq, void *stream)
+{
+    Client *c = find(g_clients, client_id);
+    if (!c) return fail(PSX_EINVAL, "unknown client id");
+    PSX_DEVICE(c->device);
+    return stream_wait_geq(stream, &c->block->applied, seq);
+}
+
+// ----------------------------------------------------------- fused round ----
+int psx_buffer_create(int device, uint64_t nbytes, uint64_t *out_id, void **out_dev_ptr)
+{
+    if (!out_id || !out_dev_ptr || nbytes == 0) return fail(PSX_EINVAL, "bad buffer arguments");
+    PSX_DEVICE(device);
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, nbytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? PSX_ENOMEM : PSX_ECUDA, "cudaMalloc(%llu): %s",
+                    (unsigned long long)nbytes, cudaGetErrorString(e));
+    }
+    CU_TRY(cudaMemset(p, 0, nbytes));
+    Buffer *b = new Buffer();
+    b->device = device;
+    b->nbytes = nbytes;
+    b->base = (char *)p;
+    uint64_t id = g_next_id.fetch_add(1);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_buffers[id] = b;
+    }
+    *out_id = id;
+    *out_dev_ptr = p;
+    return PSX_OK;
+}
+
+int psx_buffer_export(uint64_t id, void *out_handle)
+{
+    Buffer *bf = find(g_buffers, id);
+    if (!bf || !out_handle) return fail(PSX_EINVAL, "unknown buffer id or null handle");
+    HandleBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = kMagic;
+    b.abi = PSX_ABI_VERSION;
+    b.kind = KIND_BUFFER;
+    b.device = bf->device;
+    b.pid = (uint64_t)getpid();
+    b.local_id = id;
+    b.nelem = bf->nbytes;
+    PSX_DEVICE(bf->device);
+    CU_TRY(cudaIpcGetMemHandle(&b.ipc, bf->base));
+    memcpy(out_handle, &b, sizeof(b));
+    return PSX_OK;
+}
+
+int psx_buffer_destroy(uint64_t id)
+{
+    Buffer *b = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_buffers.find(id);
+        if (it == g_buffers.end()) return fail(PSX_EINVAL, "unknown buffer id");
+        b = it->second;
+        g_buffers.erase(it);
+    }
+    cudaSetDevice(b->device);
+    cudaDeviceSynchronize();
+    cudaFree(b->base);
+    delete b;
+    return PSX_OK;
+}
+
+int psx_round_bind(uint64_t shard_id, int slot, const void *grad_buf_handle,
+                   const void *param_buf_handle, uint64_t elem_off)
+{
+    Shard *s = find(g_shards, shard_id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    if (slot < 0 || slot >= PSX_MAX_SLOTS) return fail(PSX_EINVAL, "slot %d out of range", slot);
+    if (elem_off % 4) return fail(PSX_EINVAL, "elem_off must be a multiple of 4 (16-byte vectors)");
+    HandleBlob g, p;
+    int rc = check_blob(grad_buf_handle, KIND_BUFFER, &g);
+    if (rc) return rc;
+    rc = check_blob(param_buf_handle, KIND_BUFFER, &p);
+    if (rc) return rc;
+    // the kernel touches nelem_pad elements of every bound buffer
+    const uint64_t need = (elem_off + s->lay.nelem_pad) * 4;
+    if (g.nelem < need || p.nelem < need)
+        return fail(PSX_EINVAL, "bound buffers must hold %llu bytes (elem_off + padded shard), have %llu/%llu",
+                    (unsigned long long)need, (unsigned long long)g.nelem, (unsigned long long)p.nelem);
+    Bound &b = s->bound[slot];
+    if (b.valid) {
+        close_mapped(b.grad);
+        close_mapped(b.param);
+        b.valid = false;
+    }
+    rc = enable_peer(s->device, g.device);
+    if (rc) return rc;
+    rc = enable_peer(s->device, p.device);
+    if (rc) return rc;
+    rc = open_blob(g, s->device, &b.grad);
+    if (rc) return rc;
+    rc = open_blob(p, s->device, &b.param);
+    if (rc) {
+        close_mapped(b.grad);
+        return rc;
+    }
+    b.elem_off = elem_off;
+    b.valid = true;
+    return PSX_OK;
+}
+
+int psx_round(uint64_t shard_id, int mode, int first_slot, int count, uint32_t wait_seq, void *stream)
+{
+    Shard *s = find(g_shards, shard_id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    int rc = check_range(first_slot, count, PSX_MAX_SLOTS);
+    if (rc) return rc;
+    PeerSrc src;
+    memset(&src, 0, sizeof(src));
+    src.first = first_slot;
+    fill_mirrors(s, &src.peers);
+    for (int k = 0; k < count; ++k) {
+        const Bound &b = s->bound[first_slot + k];
+        if (!b.valid) return fail(PSX_ESTATE, "slot %d has no bound buffers (psx_round_bind)", first_slot + k);
+        src.peers.grad[first_slot + k] = (const float *)b.grad.base + b.elem_off;
+    }
+    for (int c = 0; c < PSX_MAX_SLOTS; ++c)  // every bound worker receives the new parameters
+        if (s->bound[c].valid)
+            src.peers.param[src.peers.n_param++] = (float *)s->bound[c].param.base + s->bound[c].elem_off;
+    PSX_DEVICE(s->device);
+    // slot flags exist for all PSX_MAX_SLOTS slots, whether or not the shard has
+    // landing slots (psx_round needs none)
+    rc = wait_slots(s, first_slot, count, wait_seq, stream);
+    if (rc) return rc;
+    return launch_apply<true>(s, mode, src, count, src.peers, (cudaStream_t)stream);
+}
+
+int psx_copy(int device, void *dst, const void *src, uint64_t nbytes, void *stream)
+{
+    if (nbytes % 4) return fail(PSX_EINVAL, "nbytes must be a multiple of 4");
+    PSX_DEVICE(device);
+    return launch_copy(dst, PSX_F32, src, PSX_F32, nbytes / 4, sm_count_of(device), nullptr, nullptr, 0,
+                       (cudaStream_t)stream);
+}
+
+}  // extern "C"

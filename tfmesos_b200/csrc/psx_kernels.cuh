@@ -1,0 +1,365 @@
+// psx_kernels.cuh -- sm_100a device code of the parameter-server data plane.
+//
+// Every kernel here is HBM- or NVLink-bound elementwise work (SURVEY.md 8d:
+// no dense contraction on the push/apply/pull path, so no tensor cores):
+//   * 128-bit vector loads/stores, fully coalesced, streaming cache hints
+//   * grids sized to the resident capacity of the 148 SMs, grid-stride loops
+//   * gradients reduced in registers in a FIXED slot order
+//   * arithmetic spelled with __f*_rn intrinsics: one IEEE-754 rounding per
+//     operation, never contracted to FMA, so results are bit-identical to the
+//     CPU restatement of TF 0.12's ApplyGradientDescent / ApplyAdam
+//   * completion published with a last-CTA ticket + st.release.sys flag so the
+//     consumer (another GPU / another process) can wait with a stream memop
+//     instead of a spinning kernel.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "psx.h"
+
+namespace psx {
+
+// ---------------------------------------------------------------- layout ----
+// First 4 KiB of every shard allocation.  Lives in the PS GPU's HBM; workers
+// map it (CUDA IPC) to publish their slot flags.
+struct ShardHeader {
+    uint32_t magic;
+    uint32_t abi;
+    float lr, b1, b2, eps;            // hyper-parameters (mnist_replica.py:147)
+    float b1p, b2p;                   // stored beta powers (AdamOptimizer._finish)
+    long long step;                   // global_step (mnist.py:46, mnist_replica.py:121)
+    unsigned int ticket;              // last-CTA counter of the apply kernels
+    unsigned int apply_seq;           // completed apply rounds
+    unsigned int slot_seq[PSX_MAX_SLOTS];  // round number last pushed into slot s
+};
+static_assert(sizeof(ShardHeader) <= 4096, "header must fit its page");
+
+// Worker-local block (in the WORKER GPU's HBM): ticket for its push kernels and
+// the mirror of the shard's apply_seq the PS writes remotely.
+struct ClientBlock {
+    unsigned int ticket;
+    unsigned int applied;             // mirror of ShardHeader::apply_seq
+    unsigned int pad[62];
+};
+
+struct PeerSet {                      // by-value kernel argument (PS address space)
+    const float *grad[PSX_MAX_SLOTS]; // bound worker gradient buffers (psx_round)
+    float *param[PSX_MAX_SLOTS];      // bound worker parameter buffers, compact
+    unsigned int *mirror[PSX_MAX_SLOTS];  // ClientBlock::applied of each client, compact
+    int n_param;
+    int n_mirror;
+};
+
+// ------------------------------------------------------------ primitives ----
+__device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// streaming (read-once) 128-bit load; works on local and peer-mapped addresses
+__device__ __forceinline__ float4 ld_stream(const float4 *p)
+{
+    float4 r;
+    asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(float4 *p, const float4 &v)
+{
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+                 "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint2 ld_stream(const uint2 *p)
+{
+    uint2 r;
+    asm volatile("ld.global.cs.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream(uint2 *p, const uint2 &v)
+{
+    asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// 4-element vectors of the two wire types
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+    using type = float4;
+    static __device__ __forceinline__ float4 load(const float *p) { return ld_stream((const float4 *)p); }
+    static __device__ __forceinline__ void store(float *p, const float4 &v) { st_stream((float4 *)p, v); }
+};
+template <> struct Vec4<__nv_bfloat16> {
+    using type = uint2;
+    static __device__ __forceinline__ float4 load(const __nv_bfloat16 *p)
+    {
+        uint2 u = ld_stream((const uint2 *)p);
+        float4 r;  // bf16 -> f32 is exact: place the 16 bits in the high half
+        r.x = __uint_as_float(u.x << 16);
+        r.y = __uint_as_float(u.x & 0xffff0000u);
+        r.z = __uint_as_float(u.y << 16);
+        r.w = __uint_as_float(u.y & 0xffff0000u);
+        return r;
+    }
+    static __device__ __forceinline__ void store(__nv_bfloat16 *p, const float4 &v)
+    {
+        // round-to-nearest-even, identical to psx_oracle_f32_to_bf16
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 u;
+        u.x = *reinterpret_cast<unsigned int *>(&lo);
+        u.y = *reinterpret_cast<unsigned int *>(&hi);
+        st_stream((uint2 *)p, u);
+    }
+};
+
+template <typename T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// Grid-wide completion: the last CTA to arrive publishes `seq` in *flag (which
+// may live in another GPU's HBM).  bar.sync, then thread 0: fence.sys (orders
+// every write of this CTA, cumulatively), ticket; the last one fences again and
+// does a release store.
+__device__ __forceinline__ bool last_cta(unsigned int *ticket)
+{
+    __shared__ bool s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    return s_last;
+}
+
+// ------------------------------------------------------------ push / pull ----
+// dst[0..n) = cast(src[0..n)).  One kernel serves PUSH (dst = slot in the PS
+// shard, possibly across NVLink) and PULL (src = var in the PS shard).  Tiles
+// of 256 threads x UNROLL vectors; all loads of a tile are issued before its
+// stores (memory-level parallelism for the ~2-3.7 us NVLink round trip).
+constexpr int kCopyThreads = 256;
+constexpr int kCopyUnroll = 4;
+
+template <typename SRC, typename DST>
+__global__ void __launch_bounds__(kCopyThreads)
+k_copy(DST *__restrict__ dst, const SRC *__restrict__ src, size_t n, int vec_ok,
+       unsigned int *ticket, unsigned int *flag, unsigned int seq)
+{
+    if (vec_ok) {
+        const size_t n4 = n >> 2;
+        const size_t tile = (size_t)kCopyThreads * kCopyUnroll;
+        const size_t tiles = (n4 + tile - 1) / tile;
+        for (size_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+            const size_t base = t * tile + threadIdx.x;
+            float4 r[kCopyUnroll];
+#pragma unroll
+            for (int u = 0; u < kCopyUnroll; ++u) {
+                size_t i = base + (size_t)u * kCopyThreads;
+                if (i < n4) r[u] = Vec4<SRC>::load(src + 4 * i);
+            }
+#pragma unroll
+            for (int u = 0; u < kCopyUnroll; ++u) {
+                size_t i = base + (size_t)u * kCopyThreads;
+                if (i < n4) Vec4<DST>::store(dst + 4 * i, r[u]);
+            }
+        }
+        // scalar tail (< 4 elements)
+        if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+            size_t i = (n4 << 2) + threadIdx.x;
+            dst[i] = from_f32<DST>(to_f32<SRC>(src[i]));
+        }
+    } else {  // unaligned sub-range: correct, not fast
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+             i += (size_t)gridDim.x * blockDim.x)
+            dst[i] = from_f32<DST>(to_f32<SRC>(src[i]));
+    }
+    if (flag != nullptr) {
+        if (last_cta(ticket) && threadIdx.x == 0) {
+            *ticket = 0;
+            __threadfence_system();
+            st_release_sys(flag, seq);
+        }
+    }
+}
+
+// one thread: release-store a flag (psx_signal)
+__global__ void k_signal(unsigned int *flag, unsigned int seq)
+{
+    __threadfence_system();
+    st_release_sys(flag, seq);
+}
+
+// --------------------------------------------------------------- optimizer ---
+// TF 0.12 ApplyGradientDescent: var -= grad * lr           (mnist.py:55)
+__device__ __forceinline__ float sgd1(float var, float g, float lr)
+{
+    return __fsub_rn(var, __fmul_rn(g, lr));
+}
+
+// TF 0.12 ApplyAdam (mnist_replica.py:147); eps outside the bias correction
+__device__ __forceinline__ void adam1(float &var, float &m, float &v, float g, float alpha,
+                                      float omb1, float omb2, float eps)
+{
+    m = __fadd_rn(m, __fmul_rn(__fsub_rn(g, m), omb1));
+    v = __fadd_rn(v, __fmul_rn(__fsub_rn(__fmul_rn(g, g), v), omb2));
+    float num = __fmul_rn(m, alpha);
+    float den = __fadd_rn(__fsqrt_rn(v), eps);
+    var = __fsub_rn(var, __fdiv_rn(num, den));
+}
+
+__device__ __forceinline__ float adam_alpha(float lr, float b1p, float b2p)
+{
+    float s = __fsqrt_rn(__fsub_rn(1.0f, b2p));
+    return __fdiv_rn(__fmul_rn(lr, s), __fsub_rn(1.0f, b1p));
+}
+
+#define PSX_FOR4(expr_x, expr_y, expr_z, expr_w) \
+    do { expr_x; expr_y; expr_z; expr_w; } while (0)
+
+template <int OPT>
+__device__ __forceinline__ void apply4(float4 &x, float4 &m, float4 &v, const float4 &g,
+                                       float lr, float alpha, float omb1, float omb2, float eps)
+{
+    if (OPT == PSX_OPT_SGD) {
+        x.x = sgd1(x.x, g.x, lr);
+        x.y = sgd1(x.y, g.y, lr);
+        x.z = sgd1(x.z, g.z, lr);
+        x.w = sgd1(x.w, g.w, lr);
+    } else {
+        adam1(x.x, m.x, v.x, g.x, alpha, omb1, omb2, eps);
+        adam1(x.y, m.y, v.y, g.y, alpha, omb1, omb2, eps);
+        adam1(x.z, m.z, v.z, g.z, alpha, omb1, omb2, eps);
+        adam1(x.w, m.w, v.w, g.w, alpha, omb1, omb2, eps);
+    }
+}
+
+__device__ __forceinline__ float4 add4(const float4 &a, const float4 &b)
+{
+    return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z),
+                       __fadd_rn(a.w, b.w));
+}
+__device__ __forceinline__ float4 div4(const float4 &a, float d)
+{
+    return make_float4(__fdiv_rn(a.x, d), __fdiv_rn(a.y, d), __fdiv_rn(a.z, d), __fdiv_rn(a.w, d));
+}
+
+constexpr int kApplyThreads = 256;
+constexpr int kSlotChunk = 4;  // gradient vectors in flight per thread
+
+// Where slot s's gradient vector i comes from.
+template <typename WIRE> struct SlotSrc {            // landing slots in the shard
+    const WIRE *base;
+    size_t stride;                                   // elements between slots
+    int first;
+    __device__ __forceinline__ float4 load(int s, size_t i) const
+    {
+        return Vec4<WIRE>::load(base + (size_t)(first + s) * stride + 4 * i);
+    }
+};
+struct PeerSrc {                                     // bound worker buffers (peer HBM)
+    PeerSet peers;
+    int first;
+    __device__ __forceinline__ float4 load(int s, size_t i) const
+    {
+        return ld_stream((const float4 *)peers.grad[first + s] + i);
+    }
+};
+
+// Fused reduce + apply over a whole shard (n4 vectors).  SCATTER: also write
+// the new parameters into every bound worker parameter buffer (psx_round).
+template <int OPT, int MODE, bool SCATTER, typename SRC>
+__global__ void __launch_bounds__(kApplyThreads, 3)
+k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restrict__ mom,
+        float4 *__restrict__ vel, SRC src, int count, size_t n4, PeerSet peers)
+{
+    __shared__ float s_alpha[PSX_MAX_SLOTS];
+    const float lr = h->lr, b1 = h->b1, b2 = h->b2, eps = h->eps;
+    const float omb1 = __fsub_rn(1.0f, b1);
+    const float omb2 = __fsub_rn(1.0f, b2);
+    if (OPT == PSX_OPT_ADAM) {
+        if (threadIdx.x == 0) {
+            float p1 = h->b1p, p2 = h->b2p;
+            const int na = (MODE == PSX_MODE_ASYNC_ORDERED) ? count : 1;
+            for (int k = 0; k < na; ++k) {
+                s_alpha[k] = adam_alpha(lr, p1, p2);
+                p1 = __fmul_rn(p1, b1);
+                p2 = __fmul_rn(p2, b2);
+            }
+        }
+        __syncthreads();
+    }
+    const float fcount = (float)count;
+
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (size_t)gridDim.x * blockDim.x) {
+        float4 x = ld_stream(var + i);
+        float4 m = make_float4(0.f, 0.f, 0.f, 0.f), v = m;
+        if (OPT == PSX_OPT_ADAM) {
+            m = ld_stream(mom + i);
+            v = ld_stream(vel + i);
+        }
+        if (MODE == PSX_MODE_ASYNC_ORDERED) {
+            for (int s0 = 0; s0 < count; s0 += kSlotChunk) {
+                float4 g[kSlotChunk];
+#pragma unroll
+                for (int k = 0; k < kSlotChunk; ++k)
+                    if (s0 + k < count) g[k] = src.load(s0 + k, i);
+#pragma unroll
+                for (int k = 0; k < kSlotChunk; ++k)
+                    if (s0 + k < count)
+                        apply4<OPT>(x, m, v, g[k], lr, OPT == PSX_OPT_ADAM ? s_alpha[s0 + k] : 0.f,
+                                    omb1, omb2, eps);
+            }
+        } else {
+            float4 acc;
+            for (int s0 = 0; s0 < count; s0 += kSlotChunk) {
+                float4 g[kSlotChunk];
+#pragma unroll
+                for (int k = 0; k < kSlotChunk; ++k)
+                    if (s0 + k < count) g[k] = src.load(s0 + k, i);
+#pragma unroll
+                for (int k = 0; k < kSlotChunk; ++k)
+                    if (s0 + k < count) acc = (s0 + k == 0) ? g[k] : add4(acc, g[k]);
+            }
+            if (MODE == PSX_MODE_SYNC_MEAN) acc = div4(acc, fcount);
+            apply4<OPT>(x, m, v, acc, lr, OPT == PSX_OPT_ADAM ? s_alpha[0] : 0.f, omb1, omb2, eps);
+        }
+        st_stream(var + i, x);
+        if (OPT == PSX_OPT_ADAM) {
+            st_stream(mom + i, m);
+            st_stream(vel + i, v);
+        }
+        if (SCATTER) {
+            for (int s = 0; s < peers.n_param; ++s)
+                st_stream((float4 *)peers.param[s] + i, x);
+        }
+    }
+
+    if (last_cta(&h->ticket) && threadIdx.x == 0) {
+        const int applies = (MODE == PSX_MODE_ASYNC_ORDERED) ? count : 1;
+        if (OPT == PSX_OPT_ADAM) {
+            float p1 = h->b1p, p2 = h->b2p;
+            for (int k = 0; k < applies; ++k) {
+                p1 = __fmul_rn(p1, b1);
+                p2 = __fmul_rn(p2, b2);
+            }
+            h->b1p = p1;
+            h->b2p = p2;
+        }
+        h->step += applies;
+        h->ticket = 0;
+        const unsigned int seq = h->apply_seq + 1;
+        __threadfence_system();
+        st_release_sys(&h->apply_seq, seq);
+        for (int c = 0; c < peers.n_mirror; ++c) st_release_sys(peers.mirror[c], seq);
+    }
+}
+
+}  // namespace psx

@@ -1,0 +1,334 @@
+"""Host side of the PS data plane: the pieces of TensorFlow's between-graph
+replication that the reference's examples use, re-expressed over libpsx.so.
+
+    replica_device_setter      examples/mnist/mnist.py:43, mnist_replica.py:116
+    GradientDescentOptimizer   mnist.py:55, matrix_factorization.py:39
+    AdamOptimizer              mnist_replica.py:147
+    ParameterServer            the process behind tf.train.Server for job 'ps'
+                               (tfmesos/server.py:51-66, mnist_replica.py:93-95)
+    Worker                     the session a worker opens on the PS devices
+                               (mnist.py:65, mnist_replica.py:183)
+
+Logical placement is the reference's: whole variables, round-robin over PS
+tasks in creation order.  Physical layout is B200-first: all variables of one
+PS task live in ONE flat f32 bucket in that GPU's HBM (one kernel per round,
+not one RPC per variable), and a bucket may additionally be striped over
+several GPUs to spread the NVLink ingress.
+"""
+from collections import OrderedDict
+
+from . import psx
+
+ALIGN = 32          # variables start on 128-byte boundaries inside a bucket
+STRIPE_ALIGN = 1024  # stripes start on 4 KiB boundaries
+
+
+class GradientDescentOptimizer(object):
+    """tf.train.GradientDescentOptimizer(learning_rate) (mnist.py:55)."""
+    opt = psx.OPT_SGD
+
+    def __init__(self, learning_rate):
+        self.learning_rate = float(learning_rate)
+        self.beta1, self.beta2, self.epsilon = 0.9, 0.999, 1e-8
+
+
+class AdamOptimizer(object):
+    """tf.train.AdamOptimizer(learning_rate) with TF's defaults (mnist_replica.py:147)."""
+    opt = psx.OPT_ADAM
+
+    def __init__(self, learning_rate=0.001, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        self.learning_rate = float(learning_rate)
+        self.beta1, self.beta2, self.epsilon = float(beta1), float(beta2), float(epsilon)
+
+
+def replica_device_setter(ps_tasks=0, cluster=None):
+    """Returns ``place(name) -> ps task index``: round-robin per variable in
+    creation order, starting at task 0 (tf.train.replica_device_setter as called
+    at mnist.py:43 with ps_tasks= and at mnist_replica.py:116 with cluster=).
+    Optimizer slots are colocated with their variable and never call this."""
+    if cluster is not None:
+        ps_tasks = len(cluster.get("ps", []))
+    state = {"next": 0}
+
+    def place(name):
+        if ps_tasks <= 0:
+            return None
+        task = state["next"] % ps_tasks
+        state["next"] += 1
+        return task
+
+    return place
+
+
+def _round_up(x, a):
+    return (x + a - 1) // a * a
+
+
+class VariableLayout(object):
+    """Which PS task owns each variable and where it sits in that task's bucket."""
+
+    def __init__(self, variables, ps_tasks, placement=None):
+        """variables: [(name, shape)] in creation order; placement: optional
+        {name: task} for explicit tf.device pinning (matrix_factorization.py:21-28)."""
+        self.ps_tasks = int(ps_tasks)
+        self.entries = OrderedDict()
+        self.bucket_nelem = [0] * self.ps_tasks
+        place = replica_device_setter(ps_tasks=self.ps_tasks)
+        for name, shape in variables:
+            numel = 1
+            for d in shape:
+                numel *= int(d)
+            if placement is not None and name in placement:
+                task = placement[name]
+            else:
+                task = place(name)
+            off = _round_up(self.bucket_nelem[task], ALIGN)
+            self.entries[name] = (task, off, tuple(int(d) for d in shape), numel)
+            self.bucket_nelem[task] = off + numel
+
+    def placement(self):
+        return OrderedDict((n, e[0]) for n, e in self.entries.items())
+
+    def names_of(self, task):
+        return [n for n, e in self.entries.items() if e[0] == task]
+
+
+def stripe_ranges(nelem, stripes):
+    """Split [0, nelem) into <= `stripes` contiguous ranges on 4 KiB boundaries."""
+    stripes = max(1, int(stripes))
+    chunk = _round_up(_round_up(nelem, stripes) // stripes, STRIPE_ALIGN)
+    out = []
+    lo = 0
+    while lo < nelem:
+        hi = min(nelem, lo + chunk)
+        out.append((lo, hi - lo))
+        lo = hi
+    return out
+
+
+class ShardSpec(object):
+    def __init__(self, task, stripe, device, off, nelem):
+        self.task, self.stripe, self.device = task, stripe, device
+        self.off, self.nelem = off, nelem
+        self.key = (task, stripe)
+
+    def __repr__(self):
+        return "ShardSpec(ps:%d/%d gpu%d [%d,+%d))" % (self.task, self.stripe, self.device,
+                                                       self.off, self.nelem)
+
+
+class Topology(object):
+    """Every shard of every PS task and the GPU it is pinned to.  Deterministic,
+    so all processes build the same object from the same arguments."""
+
+    def __init__(self, layout, ps_devices, worker_devices):
+        """ps_devices: per PS task, a device ordinal or a list of them (stripes);
+        worker_devices: device ordinal per worker index."""
+        self.layout = layout
+        self.worker_devices = list(worker_devices)
+        self.shards = []
+        for task in range(layout.ps_tasks):
+            devs = ps_devices[task]
+            if isinstance(devs, int):
+                devs = [devs]
+            n = max(1, layout.bucket_nelem[task])
+            for j, (off, cnt) in enumerate(stripe_ranges(n, len(devs))):
+                self.shards.append(ShardSpec(task, j, devs[j], off, cnt))
+
+    @property
+    def n_workers(self):
+        return len(self.worker_devices)
+
+    def shards_on(self, device):
+        return [s for s in self.shards if s.device == device]
+
+    def shards_of(self, task):
+        return [s for s in self.shards if s.task == task]
+
+
+class ParameterServer(object):
+    """One shard of one PS task, resident on one GPU."""
+
+    def __init__(self, spec, optimizer, n_workers, wire=psx.F32, landing_slots=True):
+        self.spec = spec
+        self.n_workers = int(n_workers)
+        self.shard = psx.Shard(spec.device, spec.nelem, optimizer.opt,
+                               optimizer.learning_rate, optimizer.beta1, optimizer.beta2,
+                               optimizer.epsilon,
+                               n_slots=self.n_workers if landing_slots else 0, wire=wire)
+
+    def handle(self):
+        return self.shard.export()
+
+    def apply(self, mode, wait_seq=0, stream=None, first_slot=0, count=None):
+        self.shard.apply(mode, first_slot, self.n_workers if count is None else count,
+                         wait_seq, stream)
+
+    def round(self, mode, wait_seq=0, stream=None, first_slot=0, count=None):
+        self.shard.round(mode, first_slot, self.n_workers if count is None else count,
+                         wait_seq, stream)
+
+    def close(self):
+        self.shard.destroy()
+
+
+class Worker(object):
+    """A worker's view of the whole parameter set: one flat gradient and one
+    flat parameter tensor per PS task in ITS OWN HBM (what TF keeps as the
+    worker-side copies it _Recv'd / will _Send), with per-variable views."""
+
+    def __init__(self, index, topology, handles, exportable=False):
+        """handles: {(task, stripe): shard handle bytes}."""
+        import torch
+        self.index = int(index)
+        self.topo = topology
+        self.device = topology.worker_devices[self.index]
+        self.layout = topology.layout
+        dev = torch.device("cuda", self.device)
+        self.buffers = []
+        self.grad_flat, self.param_flat = [], []
+        for task in range(self.layout.ps_tasks):
+            shards = topology.shards_of(task)
+            n = _round_up(sum(s.nelem for s in shards), STRIPE_ALIGN)
+            if exportable:      # psx_round needs IPC-exportable staging
+                g, p = psx.Buffer(self.device, n * 4), psx.Buffer(self.device, n * 4)
+                self.buffers.append((g, p))
+                self.grad_flat.append(g.tensor())
+                self.param_flat.append(p.tensor())
+            else:
+                self.grad_flat.append(torch.zeros(n, dtype=torch.float32, device=dev))
+                self.param_flat.append(torch.zeros(n, dtype=torch.float32, device=dev))
+        self.clients = OrderedDict()
+        for s in topology.shards:
+            self.clients[s.key] = psx.Client(handles[s.key], self.device, self.index)
+        self.params, self.grads = OrderedDict(), OrderedDict()
+        for name, (task, off, shape, numel) in self.layout.entries.items():
+            self.params[name] = self.param_flat[task][off:off + numel].view(shape)
+            self.grads[name] = self.grad_flat[task][off:off + numel].view(shape)
+
+    def client_handles(self):
+        return {k: c.export() for k, c in self.clients.items()}
+
+    def buffer_handles(self):
+        return [(g.export(), p.export()) for g, p in self.buffers]
+
+    def push(self, seq=0, stream=None, dtype=psx.F32):
+        """PUSH every bucket stripe into this worker's slot on its PS GPU."""
+        for s in self.topo.shards:
+            g = self.grad_flat[s.task]
+            self.clients[s.key].push(g.data_ptr() + s.off * g.element_size(), s.nelem, 0,
+                                     dtype, seq, stream)
+
+    def pull(self, wait_seq=0, stream=None, dtype=psx.F32):
+        """PULL every bucket stripe from its PS GPU into the flat parameters."""
+        for s in self.topo.shards:
+            p = self.param_flat[s.task]
+            self.clients[s.key].pull(p.data_ptr() + s.off * p.element_size(), s.nelem, 0,
+                                     dtype, wait_seq, stream)
+
+    def signal(self, seq, stream=None):
+        for c in self.clients.values():
+            c.signal(seq, stream)
+
+    def wait_applied(self, seq, stream=None):
+        for c in self.clients.values():
+            c.wait_applied(seq, stream)
+
+    def close(self):
+        for c in self.clients.values():
+            c.close()
+        self.clients.clear()
+        self.params.clear()
+        self.grads.clear()
+        self.grad_flat, self.param_flat = [], []
+        for g, p in self.buffers:
+            g.destroy()
+            p.destroy()
+        self.buffers = []
+
+
+class LocalCluster(object):
+    """All PS shards and all workers in THIS process (one or several GPUs):
+    the in-graph shape of examples/mnist/mnist.py, and what the tests and the
+    single-GPU bench use.  Multi-process deployments build the same objects per
+    process and exchange the handle blobs over the rendez-vous socket."""
+
+    def __init__(self, variables, ps_tasks, n_workers, optimizer, ps_devices=None,
+                 worker_devices=None, placement=None, wire=psx.F32, fused=False):
+        self.layout = VariableLayout(variables, ps_tasks, placement)
+        if ps_devices is None:
+            ps_devices = [0] * ps_tasks
+        if worker_devices is None:
+            worker_devices = [0] * n_workers
+        self.topo = Topology(self.layout, ps_devices, worker_devices)
+        self.servers = OrderedDict()
+        for spec in self.topo.shards:
+            self.servers[spec.key] = ParameterServer(spec, optimizer, n_workers, wire,
+                                                     landing_slots=not fused)
+        handles = {k: ps.handle() for k, ps in self.servers.items()}
+        self.workers = [Worker(i, self.topo, handles, exportable=fused)
+                        for i in range(n_workers)]
+        for w in self.workers:
+            for key, h in w.client_handles().items():
+                self.servers[key].shard.register_client(w.index, h)
+        if fused:
+            for w in self.workers:
+                for spec in self.topo.shards:
+                    g, p = w.buffers[spec.task]
+                    self.servers[spec.key].shard.round_bind(w.index, g.export(), p.export(),
+                                                            spec.off)
+        self.fused = fused
+        self.seq = 0
+
+    # -- whole-variable access on the PS (init_op / Variable.eval()) ---------
+    def set_variable(self, name, value):
+        import numpy as np
+        task, off, shape, numel = self.layout.entries[name]
+        flat = np.ascontiguousarray(value, dtype=np.float32).reshape(-1)
+        assert flat.size == numel, (name, flat.size, numel)
+        for spec in self.topo.shards_of(task):
+            lo, hi = max(off, spec.off), min(off + numel, spec.off + spec.nelem)
+            if lo < hi:
+                self.servers[spec.key].shard.set_values(psx.VAR, flat[lo - off:hi - off],
+                                                        lo - spec.off)
+
+    def get_variable(self, name, which=psx.VAR):
+        import numpy as np
+        task, off, shape, numel = self.layout.entries[name]
+        out = np.empty(numel, np.float32)
+        for spec in self.topo.shards_of(task):
+            lo, hi = max(off, spec.off), min(off + numel, spec.off + spec.nelem)
+            if lo < hi:
+                out[lo - off:hi - off] = self.servers[spec.key].shard.get_values(
+                    which, lo - spec.off, hi - lo)
+        return out.reshape(shape)
+
+    def global_step(self):
+        return next(iter(self.servers.values())).shard.state()["global_step"]
+
+    # -- one PS round over all workers' gradients ----------------------------
+    def round(self, mode, stream=None):
+        """push (all workers) -> apply (all shards) -> pull (all workers)."""
+        self.seq += 1
+        if self.fused:
+            for w in self.workers:
+                w.signal(self.seq, stream)
+            for ps in self.servers.values():
+                ps.round(mode, self.seq, stream)
+            for w in self.workers:
+                w.wait_applied(self.seq, stream)
+        else:
+            for w in self.workers:
+                w.push(self.seq, stream)
+            for ps in self.servers.values():
+                ps.apply(mode, self.seq, stream)
+            for w in self.workers:
+                w.pull(self.seq, stream)
+
+    def close(self):
+        for w in self.workers:
+            w.close()
+        for ps in self.servers.values():
+            ps.close()
+        self.servers.clear()
+        self.workers = []

@@ -1,0 +1,269 @@
+"""ctypes binding of libpsx.so (include/psx.h) -- the stub a tfmesos maintainer
+would add where tfmesos/server.py:51-66 hands the process to tf.train.Server.
+
+There is no fallback: if the library has not been built this module raises on
+first use, and without a CUDA device every compute call raises
+``RuntimeError(psx_last_error())`` (the reference's error style,
+tfmesos/scheduler.py:398).
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libpsx.so")
+
+ABI_VERSION = 3
+OPT_SGD, OPT_ADAM = 0, 1
+MODE_ASYNC_ORDERED, MODE_SUM, MODE_SYNC_MEAN = 0, 1, 2
+F32, BF16 = 0, 1
+VAR, M, V, SLOT0 = 0, 1, 2, 16
+MAX_SLOTS = 16
+HANDLE_BYTES = 128
+
+_u64 = ctypes.c_uint64
+_u32 = ctypes.c_uint32
+_i32 = ctypes.c_int
+_vp = ctypes.c_void_p
+_fp = ctypes.POINTER(ctypes.c_float)
+
+# name -> (restype, argtypes); every symbol include/psx.h declares
+SIGNATURES = {
+    "psx_abi_version": (_i32, []),
+    "psx_last_error": (ctypes.c_char_p, []),
+    "psx_device_count": (_i32, [ctypes.POINTER(_i32)]),
+    "psx_init": (_i32, [_i32]),
+    "psx_enable_peer": (_i32, [_i32, _i32]),
+    "psx_shard_create": (_i32, [_i32, _u64, _i32, _fp, _i32, _i32, ctypes.POINTER(_u64)]),
+    "psx_shard_destroy": (_i32, [_u64]),
+    "psx_shard_export": (_i32, [_u64, _vp]),
+    "psx_shard_set_hyper": (_i32, [_u64, _fp]),
+    "psx_set_values": (_i32, [_u64, _i32, _vp, _u64, _u64]),
+    "psx_get_values": (_i32, [_u64, _i32, _vp, _u64, _u64]),
+    "psx_get_state": (_i32, [_u64, _fp, _fp, ctypes.POINTER(ctypes.c_int64),
+                             ctypes.POINTER(_u32)]),
+    "psx_set_state": (_i32, [_u64, ctypes.c_float, ctypes.c_float, ctypes.c_int64]),
+    "psx_apply": (_i32, [_u64, _i32, _i32, _i32, _u32, _vp]),
+    "psx_shard_open": (_i32, [_vp, _i32, _i32, ctypes.POINTER(_u64)]),
+    "psx_shard_close": (_i32, [_u64]),
+    "psx_client_export": (_i32, [_u64, _vp]),
+    "psx_shard_register_client": (_i32, [_u64, _i32, _vp]),
+    "psx_push": (_i32, [_u64, _vp, _u64, _u64, _i32, _u32, _vp]),
+    "psx_pull": (_i32, [_u64, _vp, _u64, _u64, _i32, _u32, _vp]),
+    "psx_buffer_create": (_i32, [_i32, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_vp)]),
+    "psx_buffer_export": (_i32, [_u64, _vp]),
+    "psx_buffer_destroy": (_i32, [_u64]),
+    "psx_round_bind": (_i32, [_u64, _i32, _vp, _vp, _u64]),
+    "psx_signal": (_i32, [_u64, _u32, _vp]),
+    "psx_wait_applied": (_i32, [_u64, _u32, _vp]),
+    "psx_round": (_i32, [_u64, _i32, _i32, _i32, _u32, _vp]),
+    "psx_launch_count": (_u64, []),
+    "psx_shard_ptr": (_i32, [_u64, _i32, ctypes.POINTER(_vp)]),
+    "psx_copy": (_i32, [_i32, _vp, _vp, _u64, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises if it was never built (no CPU fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libpsx.so is missing (%s): build it with "
+                "`python -m tfmesos_b200.build`; there is no CPU fallback" % LIB_PATH)
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        if l.psx_abi_version() != ABI_VERSION:
+            raise RuntimeError("libpsx.so ABI %d, binding expects %d"
+                               % (l.psx_abi_version(), ABI_VERSION))
+        _lib = l
+    return _lib
+
+
+def last_error():
+    return lib().psx_last_error().decode("utf-8", "replace")
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("psx error %d: %s" % (rc, last_error()))
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(stream, int):
+        return stream
+    return stream.cuda_stream
+
+
+def device_count():
+    n = _i32(0)
+    _check(lib().psx_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def init(device):
+    _check(lib().psx_init(int(device)))
+
+
+def enable_peer(device, peer):
+    _check(lib().psx_enable_peer(int(device), int(peer)))
+
+
+def launch_count():
+    return int(lib().psx_launch_count())
+
+
+def _hyper(lr, beta1, beta2, epsilon):
+    return (ctypes.c_float * 4)(lr, beta1, beta2, epsilon)
+
+
+class Shard(object):
+    """PS-side handle of one shard in HBM (psx_shard_create)."""
+
+    def __init__(self, device, nelem, opt=OPT_SGD, lr=0.01, beta1=0.9, beta2=0.999,
+                 epsilon=1e-8, n_slots=1, wire=F32):
+        sid = _u64(0)
+        _check(lib().psx_shard_create(int(device), int(nelem), int(opt),
+                                      _hyper(lr, beta1, beta2, epsilon), int(n_slots),
+                                      int(wire), ctypes.byref(sid)))
+        self.id = sid.value
+        self.device = int(device)
+        self.nelem = int(nelem)
+        self.opt = int(opt)
+        self.n_slots = int(n_slots)
+        self.wire = int(wire)
+
+    def destroy(self):
+        if self.id:
+            _check(lib().psx_shard_destroy(self.id))
+            self.id = 0
+
+    def export(self):
+        buf = ctypes.create_string_buffer(HANDLE_BYTES)
+        _check(lib().psx_shard_export(self.id, buf))
+        return buf.raw
+
+    def set_hyper(self, lr, beta1=0.9, beta2=0.999, epsilon=1e-8):
+        _check(lib().psx_shard_set_hyper(self.id, _hyper(lr, beta1, beta2, epsilon)))
+
+    def set_values(self, which, host, off=0):
+        import numpy as np
+        a = np.ascontiguousarray(host, dtype=np.float32).ravel()
+        _check(lib().psx_set_values(self.id, int(which), a.ctypes.data, int(off), a.size))
+
+    def get_values(self, which, off=0, n=None):
+        import numpy as np
+        n = self.nelem - off if n is None else n
+        out = np.empty(n, np.float32)
+        _check(lib().psx_get_values(self.id, int(which), out.ctypes.data, int(off), int(n)))
+        return out
+
+    def state(self):
+        b1p, b2p = ctypes.c_float(0), ctypes.c_float(0)
+        step, seq = ctypes.c_int64(0), _u32(0)
+        _check(lib().psx_get_state(self.id, ctypes.byref(b1p), ctypes.byref(b2p),
+                                   ctypes.byref(step), ctypes.byref(seq)))
+        return {"beta1_power": b1p.value, "beta2_power": b2p.value,
+                "global_step": step.value, "apply_seq": seq.value}
+
+    def set_state(self, beta1_power, beta2_power, global_step):
+        _check(lib().psx_set_state(self.id, beta1_power, beta2_power, int(global_step)))
+
+    def ptr(self, which):
+        p = _vp(0)
+        _check(lib().psx_shard_ptr(self.id, int(which), ctypes.byref(p)))
+        return p.value
+
+    def register_client(self, slot, client_handle):
+        _check(lib().psx_shard_register_client(self.id, int(slot), client_handle))
+
+    def apply(self, mode, first_slot=0, count=1, wait_seq=0, stream=None):
+        _check(lib().psx_apply(self.id, int(mode), int(first_slot), int(count),
+                               int(wait_seq), _stream_ptr(stream)))
+
+    def round_bind(self, slot, grad_handle, param_handle, elem_off=0):
+        _check(lib().psx_round_bind(self.id, int(slot), grad_handle, param_handle,
+                                    int(elem_off)))
+
+    def round(self, mode, first_slot=0, count=1, wait_seq=0, stream=None):
+        _check(lib().psx_round(self.id, int(mode), int(first_slot), int(count),
+                               int(wait_seq), _stream_ptr(stream)))
+
+
+class Client(object):
+    """Worker-side attachment to a shard (psx_shard_open)."""
+
+    def __init__(self, handle, device, slot):
+        cid = _u64(0)
+        _check(lib().psx_shard_open(handle, int(device), int(slot), ctypes.byref(cid)))
+        self.id = cid.value
+        self.device = int(device)
+        self.slot = int(slot)
+
+    def close(self):
+        if self.id:
+            _check(lib().psx_shard_close(self.id))
+            self.id = 0
+
+    def export(self):
+        buf = ctypes.create_string_buffer(HANDLE_BYTES)
+        _check(lib().psx_client_export(self.id, buf))
+        return buf.raw
+
+    def push(self, grad_ptr, n, off=0, dtype=F32, seq=0, stream=None):
+        _check(lib().psx_push(self.id, grad_ptr, int(off), int(n), int(dtype), int(seq),
+                              _stream_ptr(stream)))
+
+    def pull(self, param_ptr, n, off=0, dtype=F32, wait_seq=0, stream=None):
+        _check(lib().psx_pull(self.id, param_ptr, int(off), int(n), int(dtype),
+                              int(wait_seq), _stream_ptr(stream)))
+
+    def signal(self, seq, stream=None):
+        _check(lib().psx_signal(self.id, int(seq), _stream_ptr(stream)))
+
+    def wait_applied(self, seq, stream=None):
+        _check(lib().psx_wait_applied(self.id, int(seq), _stream_ptr(stream)))
+
+
+class Buffer(object):
+    """Exportable device buffer (psx_buffer_create); ``tensor()`` views it as a
+    torch tensor without copying."""
+
+    def __init__(self, device, nbytes):
+        bid, p = _u64(0), _vp(0)
+        _check(lib().psx_buffer_create(int(device), int(nbytes), ctypes.byref(bid),
+                                       ctypes.byref(p)))
+        self.id = bid.value
+        self.ptr = p.value
+        self.device = int(device)
+        self.nbytes = int(nbytes)
+
+    def export(self):
+        buf = ctypes.create_string_buffer(HANDLE_BYTES)
+        _check(lib().psx_buffer_export(self.id, buf))
+        return buf.raw
+
+    def destroy(self):
+        if self.id:
+            _check(lib().psx_buffer_destroy(self.id))
+            self.id = 0
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.nbytes // 4,), "typestr": "<f4", "data": (self.ptr, False),
+                "version": 2, "strides": None}
+
+    def tensor(self):
+        import torch
+        return torch.as_tensor(self, device="cuda:%d" % self.device)
+
+
+def copy(device, dst_ptr, src_ptr, nbytes, stream=None):
+    _check(lib().psx_copy(int(device), dst_ptr, src_ptr, int(nbytes), _stream_ptr(stream)))
