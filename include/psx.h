@@ -119,6 +119,11 @@ int psx_set_state(uint64_t id, float b1p, float b2p, int64_t step);
 int psx_apply(uint64_t id, int mode, int first_slot, int count, uint32_t wait_seq,
               void *stream);
 
+/* Only the waiting half of psx_apply / psx_round: make `stream` wait until slots
+ * [first_slot, first_slot+count) carry seq >= wait_seq.  Lets a caller bracket
+ * the kernel alone with CUDA events. */
+int psx_wait_slots(uint64_t id, int first_slot, int count, uint32_t wait_seq, void *stream);
+
 /* ------------------------------------------------------------- worker side */
 
 /* Map a PS shard into this process for use from `device` as gradient slot

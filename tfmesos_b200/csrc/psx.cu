@@ -626,6 +626,16 @@ int psx_apply(uint64_t id, int mode, int first_slot, int count, uint32_t wait_se
     return launch_apply<false>(s, mode, src, count, peers, (cudaStream_t)stream);
 }
 
+int psx_wait_slots(uint64_t id, int first_slot, int count, uint32_t wait_seq, void *stream)
+{
+    Shard *s = find(g_shards, id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    int rc = check_range(first_slot, count, PSX_MAX_SLOTS);
+    if (rc) return rc;
+    PSX_DEVICE(s->device);
+    return wait_slots(s, first_slot, count, wait_seq, stream);
+}
+
 int psx_shard_register_client(uint64_t shard_id, int slot, const void *client_handle)
 {
     Shard *s = find(g_shards, shard_id);

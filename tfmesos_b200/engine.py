@@ -332,3 +332,150 @@ class LocalCluster(object):
             ps.close()
         self.servers.clear()
         self.workers = []
+
+
+class HostStaging(object):
+    """Pinned host mirrors of a worker's flat gradient / parameter tensors: the
+    reference's worker keeps these in host memory (its PS path is CPU<->CPU over
+    gRPC); with them the public round is host-in / host-out."""
+
+    def __init__(self, worker):
+        import torch
+        self.grad = [torch.empty(t.numel(), dtype=torch.float32).pin_memory()
+                     for t in worker.grad_flat]
+        self.param = [torch.empty(t.numel(), dtype=torch.float32).pin_memory()
+                      for t in worker.param_flat]
+
+    def h2d_bytes(self):
+        return sum(t.numel() * 4 for t in self.grad)
+
+    def d2h_bytes(self):
+        return sum(t.numel() * 4 for t in self.param)
+
+
+class TorchrunCluster(object):
+    """One process per GPU (launched by torchrun / tfrun): rank r is worker r on
+    GPU r and also hosts the PS shards pinned to GPU r.  Handle blobs are
+    exchanged once with all_gather_object -- torch.distributed is plumbing only;
+    nothing on the push/apply/pull path touches NCCL."""
+
+    def __init__(self, variables, ps_tasks, optimizer, placement=None, stripes=None,
+                 fused=False, wire=psx.F32, device=None):
+        import torch
+        import torch.distributed as dist
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.device = self.rank if device is None else device
+        psx.init(self.device)
+        self.layout = VariableLayout(variables, ps_tasks, placement)
+        stripes = self.world if stripes is None else max(1, min(int(stripes), self.world))
+        ps_devices = [[(t + j) % self.world for j in range(stripes)]
+                      for t in range(ps_tasks)]
+        self.topo = Topology(self.layout, ps_devices, list(range(self.world)))
+        self.fused = fused
+        self.servers = OrderedDict()
+        for spec in self.topo.shards_on(self.device):
+            self.servers[spec.key] = ParameterServer(spec, optimizer, self.world, wire,
+                                                     landing_slots=not fused)
+        handles = self._merge({k: ps.handle() for k, ps in self.servers.items()})
+        self.worker = Worker(self.rank, self.topo, handles, exportable=fused)
+        clients = self._merge({(k, self.rank): h
+                               for k, h in self.worker.client_handles().items()})
+        for (key, widx), h in clients.items():
+            if key in self.servers:
+                self.servers[key].shard.register_client(widx, h)
+        if fused:
+            bufs = self._merge({self.rank: self.worker.buffer_handles()})
+            for key, ps in self.servers.items():
+                for widx in range(self.world):
+                    g, p = bufs[widx][ps.spec.task]
+                    ps.shard.round_bind(widx, g, p, ps.spec.off)
+        self.worker_stream = torch.cuda.Stream(device=self.device)
+        self.ps_stream = torch.cuda.Stream(device=self.device)
+        # the shard whose kernel dominates a round (what a KernelTimer brackets)
+        self.dominant = max(self.servers.values(), key=lambda ps: ps.spec.nelem,
+                            default=None)
+        self.seq = 0
+        self.staging = None
+        self.barrier()
+
+    def _merge(self, mine):
+        import torch.distributed as dist
+        if self.world == 1:
+            return dict(mine)
+        out = [None] * self.world
+        dist.all_gather_object(out, mine)
+        merged = {}
+        for d in out:
+            merged.update(d)
+        return merged
+
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier()
+
+    def set_variable(self, name, value):
+        import numpy as np
+        task, off, shape, numel = self.layout.entries[name]
+        flat = np.ascontiguousarray(value, dtype=np.float32).reshape(-1)
+        for key, ps in self.servers.items():
+            spec = ps.spec
+            if spec.task != task:
+                continue
+            lo, hi = max(off, spec.off), min(off + numel, spec.off + spec.nelem)
+            if lo < hi:
+                ps.shard.set_values(psx.VAR, flat[lo - off:hi - off], lo - spec.off)
+
+    def round(self, mode, timer=None):
+        """One global PS round, fully asynchronous: worker stream = push ... pull,
+        PS stream = wait(flags) + apply; the GPUs' front ends do the ordering."""
+        self.seq += 1
+        ws, pss = self.worker_stream, self.ps_stream
+        if self.fused:
+            self.worker.signal(self.seq, ws)
+            for ps in self.servers.values():
+                ps.shard.wait_slots(0, self.world, self.seq, pss)
+                timed = timer is not None and ps is self.dominant
+                if timed:
+                    timer.start(pss)
+                ps.round(mode, 0, pss)
+                if timed:
+                    timer.stop(pss)
+            self.worker.wait_applied(self.seq, ws)
+        else:
+            self.worker.push(self.seq, ws)
+            for ps in self.servers.values():
+                ps.shard.wait_slots(0, self.world, self.seq, pss)
+                timed = timer is not None and ps is self.dominant
+                if timed:
+                    timer.start(pss)
+                ps.apply(mode, 0, pss)
+                if timed:
+                    timer.stop(pss)
+            self.worker.pull(self.seq, ws)
+
+    def round_host(self, mode):
+        """The same round from HOST buffers: H2D of this step's gradients from
+        pinned memory, the round, D2H of the refreshed parameters."""
+        import torch
+        if self.staging is None:
+            self.staging = HostStaging(self.worker)
+        st = self.staging
+        with torch.cuda.stream(self.worker_stream):
+            for dev, host in zip(self.worker.grad_flat, st.grad):
+                dev.copy_(host, non_blocking=True)
+        self.round(mode)
+        with torch.cuda.stream(self.worker_stream):
+            for dev, host in zip(self.worker.param_flat, st.param):
+                host.copy_(dev, non_blocking=True)
+
+    def close(self):
+        self.barrier()
+        self.worker.close()
+        self.barrier()
+        for ps in self.servers.values():
+            ps.close()
+        self.servers.clear()

@@ -43,6 +43,7 @@ SIGNATURES = {
                              ctypes.POINTER(_u32)]),
     "psx_set_state": (_i32, [_u64, ctypes.c_float, ctypes.c_float, ctypes.c_int64]),
     "psx_apply": (_i32, [_u64, _i32, _i32, _i32, _u32, _vp]),
+    "psx_wait_slots": (_i32, [_u64, _i32, _i32, _u32, _vp]),
     "psx_shard_open": (_i32, [_vp, _i32, _i32, ctypes.POINTER(_u64)]),
     "psx_shard_close": (_i32, [_u64]),
     "psx_client_export": (_i32, [_u64, _vp]),
@@ -187,6 +188,10 @@ class Shard(object):
     def apply(self, mode, first_slot=0, count=1, wait_seq=0, stream=None):
         _check(lib().psx_apply(self.id, int(mode), int(first_slot), int(count),
                                int(wait_seq), _stream_ptr(stream)))
+
+    def wait_slots(self, first_slot, count, wait_seq, stream=None):
+        _check(lib().psx_wait_slots(self.id, int(first_slot), int(count), int(wait_seq),
+                                    _stream_ptr(stream)))
 
     def round_bind(self, slot, grad_handle, param_handle, elem_off=0):
         _check(lib().psx_round_bind(self.id, int(slot), grad_handle, param_handle,
