@@ -60,7 +60,8 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-mnist", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--cpu-sample-elems", type=int, default=20_000_000)
+    p.add_argument("--cpu-sample-elems", type=int, default=100_000_000,
+                   help="CPU arms: parameters per step (divided by the worker count)")
     return p.parse_args()
 
 
@@ -158,8 +159,8 @@ def cpu_ps(args, steps, warmup):
     host cores, memcpy pull), on a bounded sample of the workload."""
     from oracle import ps_oracle as o
     n_full = n_params(args.workload)
-    n = min(n_full, args.cpu_sample_elems)
     W = max(1, args.gpus)           # N GPUs <-> N workers, as on the CUDA arm
+    n = min(n_full, max(1_000_000, args.cpu_sample_elems // W))
     base = o.CpuPsBaseline(n, W, o.ADAM, lr=0.01)
     mode = {"sum": o.SUM, "async": o.ASYNC_ORDERED, "mean": o.SYNC_MEAN}[args.mode]
     threads = 0
@@ -372,8 +373,18 @@ def run_b200(args):
                     "algorithmic_bytes_per_launch": bytes_per_launch,
                     "launches_timed": len(timer.pairs)}
 
+    cl.close()
+
     e2e = None
     if not args.no_e2e:
+        # same workload through the host-in / host-out public call; more, smaller
+        # shards per bucket so H2D, the kernels and D2H pipeline across shards
+        e2e_stripes = max(8, world)
+        cl = engine.TorchrunCluster(variables, ps_tasks, engine.AdamOptimizer(0.01),
+                                    placement=placement, stripes=e2e_stripes, device=local_rank)
+        cl.staging = engine.HostStaging(cl.worker)
+        for t in cl.staging.grad:
+            t.normal_(0.0, 1e-2, generator=torch.Generator().manual_seed(200 + rank))
         for _ in range(2):
             one_step(host=True)
         ms_e2e, _ = timed(max(3, steps // 2), host=True)
@@ -381,9 +392,11 @@ def run_b200(args):
         e2e = {"value": bytes_step / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s",
                "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": st.h2d_bytes(), "d2h_bytes_per_step": st.d2h_bytes(),
+               "stripes_per_bucket": e2e_stripes,
                "api": "tfmesos_b200.engine.TorchrunCluster.round_host (pinned host "
-                      "gradients in, host parameters out, per rank)"}
-    cl.close()
+                      "gradients in, host parameters out, per rank; H2D / kernels / D2H "
+                      "pipelined over the shards)"}
+        cl.close()
 
     mnist = None
     if not args.no_mnist:

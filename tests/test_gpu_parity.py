@@ -42,8 +42,12 @@ def bits(a):
 
 
 def assert_bits_equal(got, want, what):
+    """Same bits everywhere; a NaN must meet a NaN (sign/payload of a NaN are not
+    defined by IEEE-754 and differ between x86 SSE and the GPU)."""
     g, w = bits(got), bits(want)
-    bad = np.nonzero(g != w)[0]
+    both_nan = np.isnan(np.ascontiguousarray(got, F).ravel()) & \
+        np.isnan(np.ascontiguousarray(want, F).ravel())
+    bad = np.nonzero((g.ravel() != w.ravel()) & ~both_nan)[0]
     assert bad.size == 0, "%s: %d of %d elements differ, first at %d: got %r want %r" % (
         what, bad.size, g.size, bad[0], got.ravel()[bad[0]], want.ravel()[bad[0]])
 

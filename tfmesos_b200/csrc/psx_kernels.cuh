@@ -123,15 +123,18 @@ template <> __device__ __forceinline__ float from_f32<float>(float v) { return v
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
 // Grid-wide completion: the last CTA to arrive publishes `seq` in *flag (which
-// may live in another GPU's HBM).  bar.sync, then thread 0: fence.sys (orders
-// every write of this CTA, cumulatively), ticket; the last one fences again and
-// does a release store.
+// may live in another GPU's HBM).  bar.sync, then thread 0: fence at GPU scope
+// (orders every write of this CTA before its ticket, cumulatively), ticket; the
+// CTA that draws the last ticket has thereby observed all the others, issues ONE
+// system-scope fence and release-stores the flag.  (A MEMBAR.SYS costs ~3 us;
+// paying it once per kernel instead of once per CTA is what keeps 300 KB
+// MNIST-sized rounds in the 10 us range -- profiles/r01.)
 __device__ __forceinline__ bool last_cta(unsigned int *ticket)
 {
     __shared__ bool s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        __threadfence();
         unsigned int t = atomicAdd(ticket, 1u);
         s_last = (t == gridDim.x - 1);
     }

@@ -368,7 +368,10 @@ class TorchrunCluster(object):
         self.device = self.rank if device is None else device
         psx.init(self.device)
         self.layout = VariableLayout(variables, ps_tasks, placement)
-        stripes = self.world if stripes is None else max(1, min(int(stripes), self.world))
+        # stripe j of PS task t is pinned to GPU (t + j) mod world; more stripes than
+        # GPUs gives several independent shards per GPU (pipelining granularity of
+        # round_host)
+        stripes = self.world if stripes is None else max(1, int(stripes))
         ps_devices = [[(t + j) % self.world for j in range(stripes)]
                       for t in range(ps_tasks)]
         self.topo = Topology(self.layout, ps_devices, list(range(self.world)))
@@ -397,6 +400,7 @@ class TorchrunCluster(object):
                             default=None)
         self.seq = 0
         self.staging = None
+        self.h2d_stream = self.d2h_stream = None
         self.barrier()
 
     def _merge(self, mine):
@@ -458,19 +462,46 @@ class TorchrunCluster(object):
             self.worker.pull(self.seq, ws)
 
     def round_host(self, mode):
-        """The same round from HOST buffers: H2D of this step's gradients from
-        pinned memory, the round, D2H of the refreshed parameters."""
+        """The same round from HOST buffers, software-pipelined over the shards:
+        while shard i's gradients cross PCIe (H2D stream), shard i-1 is pushed /
+        applied / pulled (worker + PS streams) and shard i-2's parameters go back
+        to the host (D2H stream).  Both PCIe directions stay busy; with S shards
+        per bucket the step costs about (S+1)/S of one direction's transfer."""
         import torch
         if self.staging is None:
             self.staging = HostStaging(self.worker)
-        st = self.staging
-        with torch.cuda.stream(self.worker_stream):
-            for dev, host in zip(self.worker.grad_flat, st.grad):
-                dev.copy_(host, non_blocking=True)
-        self.round(mode)
-        with torch.cuda.stream(self.worker_stream):
-            for dev, host in zip(self.worker.param_flat, st.param):
-                host.copy_(dev, non_blocking=True)
+        if self.h2d_stream is None:
+            self.h2d_stream = torch.cuda.Stream(device=self.device)
+            self.d2h_stream = torch.cuda.Stream(device=self.device)
+        st, wk = self.staging, self.worker
+        ws, pss, hs, ds = self.worker_stream, self.ps_stream, self.h2d_stream, self.d2h_stream
+        self.seq += 1
+        seq = self.seq
+        hs.wait_stream(ws)                 # last round's pushes have read grad_flat
+        shards = self.topo.shards
+        for i in range(len(shards) + 1):
+            if i < len(shards):
+                sp = shards[i]
+                g = wk.grad_flat[sp.task][sp.off:sp.off + sp.nelem]
+                with torch.cuda.stream(hs):
+                    g.copy_(st.grad[sp.task][sp.off:sp.off + sp.nelem], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(hs)
+                ws.wait_event(ev)
+                wk.clients[sp.key].push(g.data_ptr(), sp.nelem, 0, psx.F32, seq, ws)
+                ps = self.servers.get(sp.key)
+                if ps is not None:
+                    ps.apply(mode, seq, pss)
+            if i >= 1:
+                sp = shards[i - 1]
+                p = wk.param_flat[sp.task][sp.off:sp.off + sp.nelem]
+                wk.clients[sp.key].pull(p.data_ptr(), sp.nelem, 0, psx.F32, seq, ws)
+                ev = torch.cuda.Event()
+                ev.record(ws)
+                ds.wait_event(ev)
+                with torch.cuda.stream(ds):
+                    st.param[sp.task][sp.off:sp.off + sp.nelem].copy_(p, non_blocking=True)
+        ws.wait_stream(ds)                 # the step ends when the host has the parameters
 
     def close(self):
         self.barrier()

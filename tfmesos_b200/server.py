@@ -91,6 +91,8 @@ def main(argv):
     if forwards and target in forwards:
         forward_fd = socket.create_connection(tuple(forwards[target]))
 
+    if config['cmd'] is None:
+        reserved.listen(128)      # be reachable before the scheduler hands out targets
     send(conn, 'ok')
     conn.close()
 

@@ -1,0 +1,207 @@
+"""The few TensorFlow entry points the reference's examples call, re-expressed
+over the B200 engine, so that those scripts port line by line (SURVEY.md
+appendix C).  Not a TensorFlow clone: tensors are torch tensors, the model's
+forward/backward is ordinary torch code on the worker's GPU, and only the
+PS-facing calls -- variable placement, push, optimizer apply, pull -- go through
+libpsx.so.
+
+    ClusterSpec / Server(...).join()     mnist_replica.py:85-95
+    device(), constant(), Session.run    plus.py:23-33
+    replica_device_setter, optimizers    engine.py
+    ParameterClient                      the worker's session on the PS tasks:
+        init_op / Supervisor chief-or-wait   mnist_replica.py:164-184
+        sess.run([train_step, global_step])  mnist_replica.py:198-205
+"""
+import socket
+import time
+from contextlib import contextmanager
+
+from . import endpoint, engine, psx
+from .engine import (AdamOptimizer, GradientDescentOptimizer,  # noqa: F401
+                     replica_device_setter)
+
+
+class ClusterSpec(object):
+    """tf.train.ClusterSpec({'ps': [...], 'worker': [...]})."""
+
+    def __init__(self, jobs):
+        self.jobs = {k: list(v) for k, v in dict(jobs).items()}
+
+    def get(self, name, default=None):
+        return self.jobs.get(name, default)
+
+    def job_tasks(self, name):
+        return self.jobs[name]
+
+    def __getitem__(self, name):
+        return self.jobs[name]
+
+
+class Server(object):
+    """tf.train.Server(cluster, job_name=, task_index=): binds this task's
+    address from the cluster spec; ``join()`` serves the endpoint for ever."""
+
+    def __init__(self, cluster, job_name, task_index, gpus=0):
+        if not isinstance(cluster, ClusterSpec):
+            cluster = ClusterSpec(cluster)
+        self.cluster, self.job_name, self.task_index = cluster, job_name, int(task_index)
+        addr = cluster[job_name][self.task_index]
+        self.target = 'grpc://%s' % addr
+        port = int(addr.rsplit(':', 1)[1])
+        self.listener = socket.socket()
+        self.listener.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        self.listener.bind(('', port))
+        self.endpoint = endpoint.Endpoint(job_name, self.task_index, cluster.jobs, gpus=gpus)
+
+    def join(self):
+        self.endpoint.serve(self.listener)
+
+
+# ------------------------------------------------------------------ plus.py ----
+_device_stack = [None]
+
+
+@contextmanager
+def device(name):
+    """tf.device('/job:ps/task:0')."""
+    job, task = name.strip('/').split('/')
+    _device_stack.append((job.split(':')[1], int(task.split(':')[1])))
+    try:
+        yield
+    finally:
+        _device_stack.pop()
+
+
+class Node(tuple):
+    def __add__(self, other):
+        return Node(('add', _device_stack[-1], self, other))
+
+
+def constant(value):
+    return Node(('const', _device_stack[-1], value))
+
+
+class Session(object):
+    """tf.Session(target): ``run(node)`` evaluates a (tiny) placed graph from the
+    task behind ``target``; ``call`` runs a function inside that task."""
+
+    def __init__(self, target):
+        self.target = target
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+    def run(self, node):
+        return endpoint.call(self.target, 'eval', node=node)
+
+    def call(self, fn, **kwargs):
+        return endpoint.call(self.target, 'call', fn=fn, kwargs=kwargs)
+
+
+# --------------------------------------------------------- worker-side session ---
+class ParameterClient(object):
+    """A worker task's session on the PS tasks of a cluster spec.
+
+    variables: [(name, shape)] in creation order -> placed by
+    replica_device_setter over len(cluster['ps']) tasks (or ``placement``).
+    The chief (worker 0) runs the init_op; the others wait for it, like
+    tf.train.Supervisor.prepare_or_wait_for_session (mnist_replica.py:166-184).
+    """
+
+    def __init__(self, cluster, variables, optimizer, worker_index, device=0,
+                 placement=None, init=None, wire=psx.F32):
+        import torch
+        if not isinstance(cluster, ClusterSpec):
+            cluster = ClusterSpec(cluster)
+        self.cluster = cluster
+        self.index = int(worker_index)
+        self.n_workers = len(cluster['worker'])
+        self.ps_addrs = cluster['ps']
+        self.is_chief = self.index == 0
+        self.device = device
+        psx.init(device)
+        self.layout = engine.VariableLayout(variables, len(self.ps_addrs), placement)
+        ps_devices = [endpoint.call(a, 'device') for a in self.ps_addrs]
+        # device ordinals on the PS side are irrelevant to the worker: it maps
+        # the shard by handle; the topology only records one stripe per task
+        self.topo = engine.Topology(self.layout, ps_devices,
+                                    [device] * self.n_workers)
+        hyper = (optimizer.learning_rate, optimizer.beta1, optimizer.beta2, optimizer.epsilon)
+        handles = {}
+        for spec in self.topo.shards:
+            handles[spec.key] = endpoint.call(
+                self.ps_addrs[spec.task], 'create_shard', key=spec.key, nelem=spec.nelem,
+                opt=optimizer.opt, hyper=hyper, n_slots=self.n_workers, wire=wire)
+        self.worker = engine.Worker(self.index, self.topo, handles)
+        for key, h in self.worker.client_handles().items():
+            endpoint.call(self.ps_addrs[key[0]], 'register_client', key=key,
+                          slot=self.index, handle=h)
+        self.params, self.grads = self.worker.params, self.worker.grads
+        self.stream = torch.cuda.Stream(device=device)
+        self.push_seq = 0
+        self.applied = {spec.key: 0 for spec in self.topo.shards}
+        if self.is_chief:
+            for name, value in (init or {}).items():
+                self.assign(name, value)
+            for a in self.ps_addrs:
+                endpoint.call(a, 'put', name='initialized', value=True)
+        else:
+            for a in self.ps_addrs:
+                deadline = time.time() + 300
+                while not endpoint.call(a, 'get', name='initialized', default=False):
+                    if time.time() > deadline:
+                        raise RuntimeError('chief never initialised the variables')
+                    time.sleep(0.05)
+        self.pull()
+
+    def assign(self, name, value):
+        import numpy as np
+        task, off, shape, numel = self.layout.entries[name]
+        flat = np.ascontiguousarray(value, dtype=np.float32).reshape(-1)
+        assert flat.size == numel
+        endpoint.call(self.ps_addrs[task], 'set_values', key=(task, 0), which=psx.VAR,
+                      off=off, data=flat.tobytes())
+
+    def read(self, name):
+        import numpy as np
+        task, off, shape, numel = self.layout.entries[name]
+        raw = endpoint.call(self.ps_addrs[task], 'get_values', key=(task, 0), which=psx.VAR,
+                            off=off, n=numel)
+        return np.frombuffer(raw, np.float32).reshape(shape).copy()
+
+    def pull(self):
+        """PULL (Variable reads of the next sess.run)."""
+        for spec in self.topo.shards:
+            p = self.worker.param_flat[spec.task]
+            self.worker.clients[spec.key].pull(p.data_ptr() + spec.off * 4, spec.nelem, 0,
+                                               psx.F32, self.applied[spec.key], self.stream)
+        self.stream.synchronize()
+
+    def minimize(self, mode=psx.MODE_ASYNC_ORDERED):
+        """PUSH this worker's gradients and have every PS apply them (async: this
+        worker's slot alone, one global step), then PULL the result -- one
+        ``sess.run([train_step, global_step])`` (mnist_replica.py:204)."""
+        import torch
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        self.push_seq += 1
+        self.worker.push(self.push_seq, self.stream)
+        for spec in self.topo.shards:
+            if mode == psx.MODE_ASYNC_ORDERED:
+                first, count = self.index, 1
+            else:
+                first, count = 0, self.n_workers
+            self.applied[spec.key] = endpoint.call(
+                self.ps_addrs[spec.task], 'apply', key=spec.key, mode=mode,
+                first_slot=first, count=count, wait_seq=self.push_seq)
+        self.pull()
+        return self.global_step()
+
+    def global_step(self):
+        st = endpoint.call(self.ps_addrs[0], 'state', key=(0, 0))
+        return st['global_step']
+
+    def close(self):
+        self.worker.close()
