@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PSX_ABI_VERSION 3
+#define PSX_ABI_VERSION 4
 
 /* error codes */
 #define PSX_OK 0
@@ -151,6 +151,20 @@ int psx_push(uint64_t client_id, const void *grad_dev, uint64_t off, uint64_t n,
  * Replaces: Variable read _Send/_Recv ps->worker, one RecvTensor per variable. */
 int psx_pull(uint64_t client_id, void *param_dev, uint64_t off, uint64_t n,
              int out_dtype, uint32_t wait_seq, void *stream);
+
+/* Bucketed tensor lists (BASELINE config #4: ResNet-50's 161 tensors): describe
+ * once which device tensor (dev_ptrs[i], n[i] f32 elements) lives at which
+ * shard element offset (offs[i]); afterwards ONE launch pushes / pulls the whole
+ * list.  use_tma = 1: chunks stream global -> shared -> global with bulk-async
+ * (TMA) copies through a 4-stage shared-memory ring; 0: plain 128-bit
+ * loads/stores over the same chunk table.  Tensors whose address or offset is
+ * not 16-byte aligned are copied element-wise.  f32 wire format only.
+ * Replaces: the per-variable RecvTensor RPCs of one sess.run. */
+int psx_list_create(uint64_t client_id, const void *const *dev_ptrs, const uint64_t *offs,
+                    const uint64_t *n, int count, uint64_t *out_list_id);
+int psx_list_destroy(uint64_t list_id);
+int psx_push_list(uint64_t list_id, uint32_t seq, int use_tma, void *stream);
+int psx_pull_list(uint64_t list_id, uint32_t wait_seq, int use_tma, void *stream);
 
 /* ---------------------------------------------- one-shot fused round (sync) */
 

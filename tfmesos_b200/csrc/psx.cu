@@ -168,6 +168,14 @@ struct Client {
     char *my_slot() const { return shard.base + lay.off_slots() + (size_t)slot * lay.nelem_pad * lay.wire_bytes(); }
 };
 
+struct TensorList {
+    uint64_t client_id = 0;
+    int device = 0;
+    ListChunk *d_chunks = nullptr;
+    int n_chunks = 0;
+    int sm_count = 148;
+};
+
 struct Buffer {
     int device = 0;
     uint64_t nbytes = 0;
@@ -178,6 +186,7 @@ std::mutex g_mu;
 std::unordered_map<uint64_t, Shard *> g_shards;
 std::unordered_map<uint64_t, Client *> g_clients;
 std::unordered_map<uint64_t, Buffer *> g_buffers;
+std::unordered_map<uint64_t, TensorList *> g_lists;
 std::atomic<uint64_t> g_next_id{1};
 std::atomic<uint64_t> g_launches{0};
 
@@ -785,6 +794,132 @@ int psx_wait_applied(uint64_t client_id, uint32_t seq, void *stream)
     if (!c) return fail(PSX_EINVAL, "unknown client id");
     PSX_DEVICE(c->device);
     return stream_wait_geq(stream, &c->block->applied, seq);
+}
+
+// ----------------------------------------------------------- tensor lists ---
+int psx_list_create(uint64_t client_id, const void *const *dev_ptrs, const uint64_t *offs,
+                    const uint64_t *n, int count, uint64_t *out_list_id)
+{
+    Client *c = find(g_clients, client_id);
+    if (!c) return fail(PSX_EINVAL, "unknown client id");
+    if (!dev_ptrs || !offs || !n || !out_list_id || count < 1) return fail(PSX_EINVAL, "bad list arguments");
+    if (c->lay.wire != PSX_F32) return fail(PSX_ESTATE, "tensor lists need an f32 wire format");
+    std::vector<ListChunk> chunks;
+    for (int i = 0; i < count; ++i) {
+        if (offs[i] + n[i] > c->lay.nelem)
+            return fail(PSX_EINVAL, "tensor %d: [%llu,+%llu) outside shard of %llu", i,
+                        (unsigned long long)offs[i], (unsigned long long)n[i],
+                        (unsigned long long)c->lay.nelem);
+        if (n[i] == 0) continue;
+        if (!dev_ptrs[i]) return fail(PSX_EINVAL, "tensor %d: null pointer", i);
+        char *t = (char *)dev_ptrs[i];
+        uint64_t soff = offs[i] * 4, bytes = n[i] * 4;
+        const bool aligned = ((uintptr_t)t % 16 == 0) && (soff % 16 == 0);
+        uint64_t body = aligned ? bytes / 16 * 16 : 0;
+        for (uint64_t b = 0; b < body; b += kListChunkBytes) {
+            ListChunk ch;
+            ch.tensor = t + b;
+            ch.shard_off = soff + b;
+            ch.bytes = (uint32_t)((body - b) < kListChunkBytes ? (body - b) : kListChunkBytes);
+            ch.plain = 0;
+            chunks.push_back(ch);
+        }
+        for (uint64_t b = body; b < bytes; b += kListChunkBytes) {   // ragged tail / unaligned tensor
+            ListChunk ch;
+            ch.tensor = t + b;
+            ch.shard_off = soff + b;
+            ch.bytes = (uint32_t)((bytes - b) < kListChunkBytes ? (bytes - b) : kListChunkBytes);
+            ch.plain = 1;
+            chunks.push_back(ch);
+        }
+    }
+    if (chunks.empty()) return fail(PSX_EINVAL, "empty tensor list");
+    PSX_DEVICE(c->device);
+    TensorList *l = new TensorList();
+    l->client_id = client_id;
+    l->device = c->device;
+    l->n_chunks = (int)chunks.size();
+    l->sm_count = c->sm_count;
+    cudaError_t e = cudaMalloc((void **)&l->d_chunks, chunks.size() * sizeof(ListChunk));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(l->d_chunks, chunks.data(), chunks.size() * sizeof(ListChunk), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_list_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kListStages * kListChunkBytes);
+    if (e != cudaSuccess) {
+        cudaFree(l->d_chunks);
+        delete l;
+        return fail(PSX_ECUDA, "creating tensor list: %s", cudaGetErrorString(e));
+    }
+    uint64_t id = g_next_id.fetch_add(1);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_lists[id] = l;
+    }
+    *out_list_id = id;
+    return PSX_OK;
+}
+
+int psx_list_destroy(uint64_t list_id)
+{
+    TensorList *l = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_lists.find(list_id);
+        if (it == g_lists.end()) return fail(PSX_EINVAL, "unknown list id");
+        l = it->second;
+        g_lists.erase(it);
+    }
+    cudaSetDevice(l->device);
+    cudaDeviceSynchronize();
+    cudaFree(l->d_chunks);
+    delete l;
+    return PSX_OK;
+}
+
+static int launch_list(TensorList *l, Client *c, int to_shard, int use_tma, unsigned int *flag,
+                       uint32_t seq, cudaStream_t st)
+{
+    char *base = to_shard ? c->my_slot() : (char *)c->var();
+    unsigned int *ticket = &c->block->ticket;
+    if (use_tma) {
+        // 64 KiB of shared memory per CTA -> 3 CTAs per SM
+        int grid = l->n_chunks < l->sm_count * 3 ? l->n_chunks : l->sm_count * 3;
+        k_list_tma<<<grid, kListThreads, kListStages * kListChunkBytes, st>>>(
+            l->d_chunks, l->n_chunks, base, to_shard, ticket, flag, seq);
+    } else {
+        int grid = l->n_chunks < l->sm_count * 16 ? l->n_chunks : l->sm_count * 16;
+        k_list_ldst<<<grid, kListThreads, 0, st>>>(l->d_chunks, l->n_chunks, base, to_shard, ticket,
+                                                    flag, seq);
+    }
+    LAUNCH_CHECK();
+    return PSX_OK;
+}
+
+int psx_push_list(uint64_t list_id, uint32_t seq, int use_tma, void *stream)
+{
+    TensorList *l = find(g_lists, list_id);
+    if (!l) return fail(PSX_EINVAL, "unknown list id");
+    Client *c = find(g_clients, l->client_id);
+    if (!c) return fail(PSX_ESTATE, "the list's client was closed");
+    if (c->lay.n_slots == 0) return fail(PSX_ESTATE, "shard was created without gradient slots");
+    PSX_DEVICE(c->device);
+    return launch_list(l, c, 1, use_tma, seq ? &c->hdr()->slot_seq[c->slot] : nullptr, seq,
+                       (cudaStream_t)stream);
+}
+
+int psx_pull_list(uint64_t list_id, uint32_t wait_seq, int use_tma, void *stream)
+{
+    TensorList *l = find(g_lists, list_id);
+    if (!l) return fail(PSX_EINVAL, "unknown list id");
+    Client *c = find(g_clients, l->client_id);
+    if (!c) return fail(PSX_ESTATE, "the list's client was closed");
+    PSX_DEVICE(c->device);
+    if (wait_seq) {
+        int rc = stream_wait_geq(stream, &c->block->applied, wait_seq);
+        if (rc) return rc;
+    }
+    return launch_list(l, c, 0, use_tma, nullptr, 0, (cudaStream_t)stream);
 }
 
 // ----------------------------------------------------------- fused round ----

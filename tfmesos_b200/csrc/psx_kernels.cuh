@@ -192,6 +192,166 @@ k_copy(DST *__restrict__ dst, const SRC *__restrict__ src, size_t n, int vec_ok,
     }
 }
 
+// ------------------------------------------------------- tensor lists (TMA) ----
+// A model's parameters are a LIST of tensors (ResNet-50: 161, 107 of them
+// <= 2048 elements).  One launch moves the whole list between the worker's
+// separate tensors and their places in the flat shard: the host cuts every
+// tensor into <= 16 KiB chunks once (psx_list_create); each CTA streams its
+// chunks global -> shared -> global with bulk-async (TMA) copies through a
+// 4-stage shared-memory ring -- one elected thread drives the copy engine, no
+// registers or LSU instructions are spent on the data.
+struct ListChunk {
+    char *tensor;              // worker-side address of this chunk
+    uint64_t shard_off;        // byte offset inside the slot / var region
+    uint32_t bytes;            // multiple of 16 for TMA chunks
+    uint32_t plain;            // 1: not 16 B aligned -> element loop by the whole CTA
+};
+
+constexpr int kListStages = 4;
+constexpr uint32_t kListChunkBytes = 16384;
+constexpr int kListThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *smem_dst, const void *gsrc, uint32_t bytes,
+                                            uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+
+// to_shard = 1: PUSH (tensor -> shard_base + off), 0: PULL (shard_base + off -> tensor)
+__global__ void __launch_bounds__(kListThreads)
+k_list_tma(const ListChunk *__restrict__ chunks, int n_chunks, char *shard_base, int to_shard,
+           unsigned int *ticket, unsigned int *flag, unsigned int seq)
+{
+    extern __shared__ __align__(128) unsigned char ring[];
+    __shared__ __align__(8) uint64_t full[kListStages];
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kListStages; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int mine = (n_chunks - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto chunk_of = [&](int j) { return chunks[(size_t)blockIdx.x + (size_t)j * gridDim.x]; };
+
+    if (threadIdx.x == 0) {
+        constexpr int D = kListStages - 1;            // loads kept in flight
+        auto issue_load = [&](int j) {
+            const ListChunk c = chunk_of(j);
+            if (c.plain) return;
+            const int s = j % kListStages;
+            const char *src = to_shard ? c.tensor : shard_base + c.shard_off;
+            mbar_expect_tx(&full[s], c.bytes);
+            tma_load_1d(ring + (size_t)s * kListChunkBytes, src, c.bytes, &full[s]);
+        };
+        for (int j = 0; j < D && j < mine; ++j) issue_load(j);
+        for (int j = 0; j < mine; ++j) {
+            if (j + D < mine) {
+                // stage (j+D)%S was read by chunk j-1's store: wait until it has been read
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                issue_load(j + D);
+            }
+            const ListChunk c = chunk_of(j);
+            if (c.plain) continue;
+            const int s = j % kListStages;
+            mbar_wait(&full[s], (uint32_t)((j / kListStages) & 1));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            char *dst = to_shard ? shard_base + c.shard_off : c.tensor;
+            tma_store_1d(dst, ring + (size_t)s * kListChunkBytes, c.bytes);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores performed
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    // ragged / unaligned tensors: plain element loop by the whole CTA
+    for (int j = 0; j < mine; ++j) {
+        const ListChunk c = chunk_of(j);
+        if (!c.plain) continue;
+        const float *src = (const float *)(to_shard ? c.tensor : shard_base + c.shard_off);
+        float *dst = (float *)(to_shard ? shard_base + c.shard_off : c.tensor);
+        for (uint32_t i = threadIdx.x; i < c.bytes / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    if (flag != nullptr) {
+        if (last_cta(ticket) && threadIdx.x == 0) {
+            *ticket = 0;
+            __threadfence_system();
+            st_release_sys(flag, seq);
+        }
+    }
+}
+
+// same table, plain 128-bit loads/stores (the non-TMA baseline of the list path)
+__global__ void __launch_bounds__(kListThreads)
+k_list_ldst(const ListChunk *__restrict__ chunks, int n_chunks, char *shard_base, int to_shard,
+            unsigned int *ticket, unsigned int *flag, unsigned int seq)
+{
+    for (int j = blockIdx.x; j < n_chunks; j += gridDim.x) {
+        const ListChunk c = chunks[j];
+        const char *src = to_shard ? c.tensor : shard_base + c.shard_off;
+        char *dst = to_shard ? shard_base + c.shard_off : c.tensor;
+        if (c.plain) {
+            for (uint32_t i = threadIdx.x; i < c.bytes / 4; i += blockDim.x)
+                ((float *)dst)[i] = ((const float *)src)[i];
+        } else {
+            const uint32_t n16 = c.bytes / 16;
+            for (uint32_t i = threadIdx.x; i < n16; i += 4 * blockDim.x) {
+                float4 r[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i + u * blockDim.x < n16) r[u] = ld_stream((const float4 *)src + i + u * blockDim.x);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i + u * blockDim.x < n16) st_stream((float4 *)dst + i + u * blockDim.x, r[u]);
+            }
+        }
+    }
+    if (flag != nullptr) {
+        if (last_cta(ticket) && threadIdx.x == 0) {
+            *ticket = 0;
+            __threadfence_system();
+            st_release_sys(flag, seq);
+        }
+    }
+}
+
 // one thread: release-store a flag (psx_signal)
 __global__ void k_signal(unsigned int *flag, unsigned int seq)
 {

@@ -510,3 +510,44 @@ class TorchrunCluster(object):
         for ps in self.servers.values():
             ps.close()
         self.servers.clear()
+
+
+class TensorListBinding(object):
+    """A model's own (separate) tensors bound to their places in the PS buckets:
+    ``push`` / ``pull`` move the whole list with ONE kernel launch per shard
+    (psx_push_list / psx_pull_list, TMA-staged) instead of one copy per variable
+    -- the reference issues one RecvTensor RPC per variable per direction."""
+
+    def __init__(self, worker, tensors):
+        """tensors: {variable name: contiguous float32 CUDA tensor of that shape}."""
+        self.worker = worker
+        self.keep = dict(tensors)              # keep the storages alive
+        self.lists = OrderedDict()
+        for spec in worker.topo.shards:
+            ptrs, offs, counts = [], [], []
+            for name, (task, off, shape, numel) in worker.layout.entries.items():
+                if task != spec.task or name not in tensors:
+                    continue
+                t = tensors[name]
+                assert t.is_contiguous() and t.numel() == numel and t.element_size() == 4, name
+                lo, hi = max(off, spec.off), min(off + numel, spec.off + spec.nelem)
+                if lo < hi:
+                    ptrs.append(t.data_ptr() + (lo - off) * 4)
+                    offs.append(lo - spec.off)
+                    counts.append(hi - lo)
+            if ptrs:
+                self.lists[spec.key] = psx.TensorList(worker.clients[spec.key], ptrs, offs, counts)
+
+    def push(self, seq=0, tma=True, stream=None):
+        for lst in self.lists.values():
+            lst.push(seq, tma, stream)
+
+    def pull(self, wait_seq=0, tma=True, stream=None):
+        for lst in self.lists.values():
+            lst.pull(wait_seq, tma, stream)
+
+    def close(self):
+        for lst in self.lists.values():
+            lst.destroy()
+        self.lists.clear()
+        self.keep.clear()

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libpsx.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 OPT_SGD, OPT_ADAM = 0, 1
 MODE_ASYNC_ORDERED, MODE_SUM, MODE_SYNC_MEAN = 0, 1, 2
 F32, BF16 = 0, 1
@@ -50,6 +50,11 @@ SIGNATURES = {
     "psx_shard_register_client": (_i32, [_u64, _i32, _vp]),
     "psx_push": (_i32, [_u64, _vp, _u64, _u64, _i32, _u32, _vp]),
     "psx_pull": (_i32, [_u64, _vp, _u64, _u64, _i32, _u32, _vp]),
+    "psx_list_create": (_i32, [_u64, ctypes.POINTER(_vp), ctypes.POINTER(_u64),
+                               ctypes.POINTER(_u64), _i32, ctypes.POINTER(_u64)]),
+    "psx_list_destroy": (_i32, [_u64]),
+    "psx_push_list": (_i32, [_u64, _u32, _i32, _vp]),
+    "psx_pull_list": (_i32, [_u64, _u32, _i32, _vp]),
     "psx_buffer_create": (_i32, [_i32, _u64, ctypes.POINTER(_u64), ctypes.POINTER(_vp)]),
     "psx_buffer_export": (_i32, [_u64, _vp]),
     "psx_buffer_destroy": (_i32, [_u64]),
@@ -235,6 +240,30 @@ class Client(object):
 
     def wait_applied(self, seq, stream=None):
         _check(lib().psx_wait_applied(self.id, int(seq), _stream_ptr(stream)))
+
+
+class TensorList(object):
+    """A list of device tensors mapped onto shard offsets (psx_list_create):
+    one launch pushes / pulls all of them."""
+
+    def __init__(self, client, ptrs, offs, counts):
+        k = len(ptrs)
+        lid = _u64(0)
+        _check(lib().psx_list_create(client.id, (_vp * k)(*ptrs), (_u64 * k)(*offs),
+                                     (_u64 * k)(*counts), k, ctypes.byref(lid)))
+        self.id = lid.value
+        self.client = client
+
+    def push(self, seq=0, tma=True, stream=None):
+        _check(lib().psx_push_list(self.id, int(seq), int(bool(tma)), _stream_ptr(stream)))
+
+    def pull(self, wait_seq=0, tma=True, stream=None):
+        _check(lib().psx_pull_list(self.id, int(wait_seq), int(bool(tma)), _stream_ptr(stream)))
+
+    def destroy(self):
+        if self.id:
+            _check(lib().psx_list_destroy(self.id))
+            self.id = 0
 
 
 class Buffer(object):

@@ -190,12 +190,18 @@ class ParameterClient(object):
         self.worker.push(self.push_seq, self.stream)
         for spec in self.topo.shards:
             if mode == psx.MODE_ASYNC_ORDERED:
-                first, count = self.index, 1
+                # this worker's gradient alone: one ApplyAdam, one global step
+                self.applied[spec.key] = endpoint.call(
+                    self.ps_addrs[spec.task], 'apply', key=spec.key, mode=mode,
+                    first_slot=self.index, count=1, wait_seq=self.push_seq)
             else:
-                first, count = 0, self.n_workers
-            self.applied[spec.key] = endpoint.call(
-                self.ps_addrs[spec.task], 'apply', key=spec.key, mode=mode,
-                first_slot=first, count=count, wait_seq=self.push_seq)
+                # aggregated modes: the chief triggers the single apply of the
+                # round (SyncReplicasOptimizer's chief queue runner,
+                # mnist_replica.py:159-162,186-190); everyone waits for round n
+                if self.is_chief:
+                    endpoint.call(self.ps_addrs[spec.task], 'apply', key=spec.key, mode=mode,
+                                  first_slot=0, count=self.n_workers, wait_seq=self.push_seq)
+                self.applied[spec.key] = self.push_seq
         self.pull()
         return self.global_step()
 
