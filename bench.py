@@ -52,12 +52,13 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="nmf_scaled", choices=sorted(WORKLOADS))
     p.add_argument("--mode", default="sum", choices=sorted(MODES))
-    p.add_argument("--path", default="staged", choices=["staged", "fused"],
+    p.add_argument("--path", default="fused", choices=["staged", "fused"],
                    help="staged = push kernel + apply kernel + pull kernel; "
                         "fused = one PS-side gather/apply/scatter kernel (psx_round)")
     p.add_argument("--stripes", type=int, default=None,
                    help="GPUs each bucket is striped over (default: all)")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-staged", action="store_true")
     p.add_argument("--no-mnist", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-elems", type=int, default=100_000_000,
@@ -73,6 +74,22 @@ def n_params(workload):
             k *= d
         total += k
     return total
+
+
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the cores next to its GPU so that the pinned staging
+    buffers (first touch) and the copy-engine traffic stay on the GPU's socket."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
 
 
 # ------------------------------------------------------------------ clocks ----
@@ -234,19 +251,42 @@ def mnist_section(torch, engine, psx, world, rank, dist, steps=100, warmup=10):
     wk = cl.worker
     ws = cl.worker_stream
 
+    def fwd_bwd():
+        x.uniform_(0.0, 1.0)                    # a fresh synthetic batch every step
+        ps = [wk.params[k].detach().requires_grad_(True) for k in names]
+        h = torch.relu(x @ ps[0] + ps[1])
+        p = torch.softmax(h @ ps[2] + ps[3], 1)
+        loss = -(y * torch.log(torch.clamp(p, 1e-10, 1.0))).sum()
+        grads = torch.autograd.grad(loss, ps)
+        for k, gr in zip(names, grads):
+            wk.grads[k].copy_(gr)
+
+    graph = None
+
     def step():
         with torch.cuda.stream(ws):
-            ps = [wk.params[k].detach().requires_grad_(True) for k in names]
-            h = torch.relu(x @ ps[0] + ps[1])
-            p = torch.softmax(h @ ps[2] + ps[3], 1)
-            loss = -(y * torch.log(torch.clamp(p, 1e-10, 1.0))).sum()
-            grads = torch.autograd.grad(loss, ps)
-            for k, gr in zip(names, grads):
-                wk.grads[k].copy_(gr)
+            if graph is not None:
+                graph.replay()
+            else:
+                fwd_bwd()
         cl.round(psx.MODE_ASYNC_ORDERED)
 
     with torch.cuda.stream(ws):
         wk.pull(0, ws)
+    for _ in range(warmup):
+        step()
+    cl.barrier()
+    # the worker's compute is launch-bound (20-odd tiny kernels): capture it once
+    # in a CUDA graph; the PS round stays ordinary launches (its sequence numbers
+    # change every step)
+    try:
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_, stream=ws):
+            fwd_bwd()
+        graph = g_
+    except Exception as exc:                    # keep measuring, eagerly
+        sys.stderr.write("mnist: CUDA graph capture failed (%s), running eagerly\n" % exc)
+        graph = None
     for _ in range(warmup):
         step()
     cl.barrier()
@@ -257,12 +297,13 @@ def mnist_section(torch, engine, psx, world, rank, dist, steps=100, warmup=10):
     ev1.record(ws)
     cl.barrier()
     dt = ev0.elapsed_time(ev1) * 1e-3
-    t = torch.tensor([dt], device="cuda")
+    t = torch.tensor([dt], dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     out = {"global_steps_per_sec": steps * world / t.item(), "rounds": steps,
            "workers": world, "params": n_params("mnist_mlp"),
            "model": "784-100-10 MLP, batch 100, Adam 0.01, async-ordered",
+           "worker_compute": "CUDA graph" if graph is not None else "eager",
            "timing": "CUDA events on the worker stream over %d rounds, max over ranks" % steps}
     cl.close()
     return out
@@ -279,9 +320,13 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    all_cpus = os.sched_getaffinity(0)
+    bind_to_gpu_numa_node(local_rank)
     if world > 1:
+        # plumbing only (handle exchange, barriers, max-over-ranks): gloo over
+        # loopback -- nothing on the measured path uses a collective library
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("gloo")
     steps, warmup = max(1, args.steps), max(3, args.warmup)
     mode = MODES[args.mode]
     variables, ps_tasks, placement = WORKLOADS[args.workload]
@@ -319,9 +364,8 @@ def run_b200(args):
             one_step(timer, host)
         ev1.record(cl.worker_stream)
         cl.barrier()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
-        launches = torch.tensor([psx.launch_count() - launches0], device="cuda",
-                                dtype=torch.float64)
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64)
+        launches = torch.tensor([psx.launch_count() - launches0], dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             dist.all_reduce(launches, op=dist.ReduceOp.SUM)
@@ -372,8 +416,42 @@ def run_b200(args):
                     "algorithmic_bytes_per_elem": per_elem,
                     "algorithmic_bytes_per_launch": bytes_per_launch,
                     "launches_timed": len(timer.pairs)}
-
+        if world > 1 and args.path == "fused":
+            # the one-shot kernel is bound by this GPU's NVLink port, not by HBM:
+            # per direction it carries (N-1) remote gradient stripes in + the
+            # other owners' parameter stripes in (and the mirror image out)
+            nvl_bytes = 2 * (world - 1) * shard_elems * 4
+            nvl = nvl_bytes / (k_ms * 1e-3) / 1e9
+            roofline.update({"bound": "nvlink", "achieved": nvl, "peak": 770.0,
+                             "frac": nvl / 770.0,
+                             "peak_source": "measured peer copy per direction "
+                                            "(B200_PROFILING.md)",
+                             "nvlink_bytes_per_direction_per_launch": nvl_bytes,
+                             "hbm_achieved": achieved, "hbm_frac": achieved / hbm_peak})
     cl.close()
+
+    staged = None
+    if args.path == "fused" and not args.no_staged:
+        # the three-kernel path (push -> landing slot, reduce+apply, pull), the one
+        # asynchronous / cross-process workers use; reported beside the headline
+        cl = engine.TorchrunCluster(variables, ps_tasks, engine.AdamOptimizer(0.01),
+                                    placement=placement, stripes=args.stripes, device=local_rank)
+        for t in cl.worker.grad_flat:
+            t.copy_(torch.randn(t.numel(), device="cuda", generator=gen) * 1e-2)
+        for _ in range(warmup):
+            one_step()
+        t2 = KernelTimer()
+        ms_staged, l_staged = timed(max(3, steps // 2), timer=t2)
+        se = ((cl.dominant.spec.nelem + 1023) // 1024) * 1024
+        per = 24 + 4 * world
+        staged = {"value": bytes_step / (ms_staged * 1e-3) / 1e9, "unit": "GB/s",
+                  "ms_per_step": ms_staged, "gpu_launches": l_staged,
+                  "apply_kernel": {"kernel": "k_apply<ADAM,%s,SlotSrc<f32>>" % args.mode,
+                                   "avg_launch_ms": t2.mean_ms(),
+                                   "algorithmic_bytes_per_elem": per,
+                                   "achieved": per * se / (t2.mean_ms() * 1e-3) / 1e9,
+                                   "frac": per * se / (t2.mean_ms() * 1e-3) / 1e9 / hbm_peak}}
+        cl.close()
 
     e2e = None
     if not args.no_e2e:
@@ -404,6 +482,7 @@ def run_b200(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)          # the CPU arm gets every host core
         cb = cpu_ps(args, steps=5, warmup=1)
         cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
@@ -418,6 +497,7 @@ def run_b200(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
+            "staged_path": staged,
             "e2e": e2e,
             "cpu_baseline": cpu,
             "mnist_replica": mnist,

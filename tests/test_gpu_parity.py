@@ -460,6 +460,7 @@ def test_launch_counter_counts_this_librarys_kernels():
     torch = _torch()
     shard = psx.Shard(0, 4096, psx.OPT_SGD, n_slots=1)
     c = psx.Client(shard.export(), 0, 0)
+    shard.register_client(0, c.export())       # the pull below waits on this client's mirror
     try:
         g = torch.zeros(4096, device="cuda")
         before = psx.launch_count()
