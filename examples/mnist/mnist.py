@@ -74,12 +74,13 @@ def main():
     ]
     lock = RLock()
     rng = np.random.default_rng(0)
-    centers = rng.random((10, 784)).astype(np.float32)
+    # synthetic "digits" with MNIST-like statistics: sparse strokes, values in [0, 1]
+    centers = ((rng.random((10, 784)) < 0.2) * 0.8).astype(np.float32)
 
-    def next_batch(n):                      # separable synthetic "digits"
+    def next_batch(n):
         labels = rng.integers(0, 10, n)
-        xs = (centers[labels] + 0.3 * rng.standard_normal((n, 784))).astype(np.float32)
-        return xs, np.eye(10, dtype=np.float32)[labels]
+        xs = np.clip(centers[labels] + 0.1 * rng.standard_normal((n, 784)), 0.0, 1.0)
+        return xs.astype(np.float32), np.eye(10, dtype=np.float32)[labels]
 
     with cluster(jobs_def, quiet=True) as c:
         sessions = [tf.Session(c.targets['/job:worker/task:%d' % i]) for i in range(nworker)]

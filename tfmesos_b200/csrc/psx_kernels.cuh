@@ -273,7 +273,7 @@ k_list_tma(const ListChunk *__restrict__ chunks, int n_chunks, char *shard_base,
     auto chunk_of = [&](int j) { return chunks[(size_t)blockIdx.x + (size_t)j * gridDim.x]; };
 
     if (threadIdx.x == 0) {
-        constexpr int D = kListStages - 1;            // loads kept in flight
+        constexpr int D = kListStages - 2;            // loads kept in flight
         auto issue_load = [&](int j) {
             const ListChunk c = chunk_of(j);
             if (c.plain) return;
@@ -285,12 +285,16 @@ k_list_tma(const ListChunk *__restrict__ chunks, int n_chunks, char *shard_base,
         for (int j = 0; j < D && j < mine; ++j) issue_load(j);
         for (int j = 0; j < mine; ++j) {
             if (j + D < mine) {
-                // stage (j+D)%S was read by chunk j-1's store: wait until it has been read
-                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                // stage (j+D)%S was last read by chunk j-2's store; one bulk group is
+                // committed per iteration, so "all but the newest" covers it
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 issue_load(j + D);
             }
             const ListChunk c = chunk_of(j);
-            if (c.plain) continue;
+            if (c.plain) {
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // keep the count
+                continue;
+            }
             const int s = j % kListStages;
             mbar_wait(&full[s], (uint32_t)((j / kListStages) & 1));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -418,6 +422,7 @@ constexpr int kSlotChunk = 4;  // gradient vectors in flight per thread
 
 // Where slot s's gradient vector i comes from.
 template <typename WIRE> struct SlotSrc {            // landing slots in the shard
+    static constexpr bool kPrefetch = false;         // local HBM: occupancy hides the latency
     const WIRE *base;
     size_t stride;                                   // elements between slots
     int first;
@@ -427,6 +432,7 @@ template <typename WIRE> struct SlotSrc {            // landing slots in the sha
     }
 };
 struct PeerSrc {                                     // bound worker buffers (peer HBM)
+    static constexpr bool kPrefetch = true;          // NVLink round trip: prefetch one iteration
     PeerSet peers;
     int first;
     __device__ __forceinline__ float4 load(int s, size_t i) const
@@ -460,37 +466,62 @@ k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restric
     }
     const float fcount = (float)count;
 
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-         i += (size_t)gridDim.x * blockDim.x) {
+    // Software pipeline: the first kSlotChunk gradient vectors of the NEXT
+    // iteration are requested before this iteration's arithmetic.  With peer
+    // sources (psx_round over NVLink, ~2-3.7 us per load) this doubles the bytes
+    // each SM keeps in flight -- measured at N=2: 12 KB/SM in flight capped the
+    // gather at ~615 GB/s (profiles/r02).
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    constexpr bool PF = SRC::kPrefetch;
+    float4 gn[kSlotChunk];
+    if (PF && i < n4) {
+#pragma unroll
+        for (int k = 0; k < kSlotChunk; ++k)
+            if (k < count) gn[k] = src.load(k, i);
+    }
+    for (; i < n4; i += stride) {
         float4 x = ld_stream(var + i);
         float4 m = make_float4(0.f, 0.f, 0.f, 0.f), v = m;
         if (OPT == PSX_OPT_ADAM) {
             m = ld_stream(mom + i);
             v = ld_stream(vel + i);
         }
-        if (MODE == PSX_MODE_ASYNC_ORDERED) {
-            for (int s0 = 0; s0 < count; s0 += kSlotChunk) {
-                float4 g[kSlotChunk];
+        float4 g[kSlotChunk];
+        if (PF) {
+#pragma unroll
+            for (int k = 0; k < kSlotChunk; ++k) g[k] = gn[k];
+            const size_t inext = i + stride;
+            if (inext < n4) {
+#pragma unroll
+                for (int k = 0; k < kSlotChunk; ++k)
+                    if (k < count) gn[k] = src.load(k, inext);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kSlotChunk; ++k)
+                if (k < count) g[k] = src.load(k, i);
+        }
+        float4 acc;
+        for (int s0 = 0; s0 < count; s0 += kSlotChunk) {
+            if (s0 > 0) {
 #pragma unroll
                 for (int k = 0; k < kSlotChunk; ++k)
                     if (s0 + k < count) g[k] = src.load(s0 + k, i);
+            }
+            if (MODE == PSX_MODE_ASYNC_ORDERED) {
 #pragma unroll
                 for (int k = 0; k < kSlotChunk; ++k)
                     if (s0 + k < count)
                         apply4<OPT>(x, m, v, g[k], lr, OPT == PSX_OPT_ADAM ? s_alpha[s0 + k] : 0.f,
                                     omb1, omb2, eps);
-            }
-        } else {
-            float4 acc;
-            for (int s0 = 0; s0 < count; s0 += kSlotChunk) {
-                float4 g[kSlotChunk];
-#pragma unroll
-                for (int k = 0; k < kSlotChunk; ++k)
-                    if (s0 + k < count) g[k] = src.load(s0 + k, i);
+            } else {
 #pragma unroll
                 for (int k = 0; k < kSlotChunk; ++k)
                     if (s0 + k < count) acc = (s0 + k == 0) ? g[k] : add4(acc, g[k]);
             }
+        }
+        if (MODE != PSX_MODE_ASYNC_ORDERED) {
             if (MODE == PSX_MODE_SYNC_MEAN) acc = div4(acc, fcount);
             apply4<OPT>(x, m, v, acc, lr, OPT == PSX_OPT_ADAM ? s_alpha[0] : 0.f, omb1, omb2, eps);
         }

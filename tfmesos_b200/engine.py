@@ -353,6 +353,27 @@ class HostStaging(object):
         return sum(t.numel() * 4 for t in self.param)
 
 
+def merge_across_ranks(mine):
+    """all_gather a dict from every rank and merge them (handle exchange)."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return dict(mine)
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, mine)
+    merged = {}
+    for d in out:
+        merged.update(d)
+    return merged
+
+
+def torchrun_topology(layout, world, stripes=None):
+    """Stripe j of PS task t is pinned to GPU (t + j) mod world; worker r runs on
+    GPU r.  Same arguments -> same topology on every rank."""
+    stripes = world if stripes is None else max(1, int(stripes))
+    ps_devices = [[(t + j) % world for j in range(stripes)] for t in range(layout.ps_tasks)]
+    return Topology(layout, ps_devices, list(range(world)))
+
+
 class TorchrunCluster(object):
     """One process per GPU (launched by torchrun / tfrun): rank r is worker r on
     GPU r and also hosts the PS shards pinned to GPU r.  Handle blobs are
@@ -368,13 +389,9 @@ class TorchrunCluster(object):
         self.device = self.rank if device is None else device
         psx.init(self.device)
         self.layout = VariableLayout(variables, ps_tasks, placement)
-        # stripe j of PS task t is pinned to GPU (t + j) mod world; more stripes than
-        # GPUs gives several independent shards per GPU (pipelining granularity of
-        # round_host)
-        stripes = self.world if stripes is None else max(1, int(stripes))
-        ps_devices = [[(t + j) % self.world for j in range(stripes)]
-                      for t in range(ps_tasks)]
-        self.topo = Topology(self.layout, ps_devices, list(range(self.world)))
+        # more stripes than GPUs gives several independent shards per GPU (the
+        # pipelining granularity of round_host)
+        self.topo = torchrun_topology(self.layout, self.world, stripes)
         self.fused = fused
         self.servers = OrderedDict()
         for spec in self.topo.shards_on(self.device):
@@ -404,15 +421,7 @@ class TorchrunCluster(object):
         self.barrier()
 
     def _merge(self, mine):
-        import torch.distributed as dist
-        if self.world == 1:
-            return dict(mine)
-        out = [None] * self.world
-        dist.all_gather_object(out, mine)
-        merged = {}
-        for d in out:
-            merged.update(d)
-        return merged
+        return merge_across_ranks(mine)
 
     def barrier(self):
         import torch
