@@ -57,6 +57,9 @@ def parse():
                         "fused = one PS-side gather/apply/scatter kernel (psx_round)")
     p.add_argument("--stripes", type=int, default=None,
                    help="GPUs each bucket is striped over (default: all)")
+    p.add_argument("--wire", default="f32", choices=["f32", "bf16"],
+                   help="element type of the workers' gradient/parameter tensors "
+                        "(the PS master is always f32; bf16 = BASELINE config #4)")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-staged", action="store_true")
     p.add_argument("--no-mnist", action="store_true")
@@ -221,7 +224,7 @@ def run_reference(args):
 def workload_config(args, world, n_full):
     return {"workload": "%s: PS round (push+reduce/apply+pull) over %d f32 parameters, Adam(lr=0.01)"
                         % (args.workload, n_full),
-            "discipline": args.mode, "path": args.path,
+            "discipline": args.mode, "path": args.path, "wire": args.wire,
             "parallelism": "%d workers (1/GPU), %d ps tasks, buckets striped over %s GPU(s)"
                            % (world, WORKLOADS[args.workload][1],
                               args.stripes if args.stripes else world),
@@ -332,9 +335,11 @@ def run_b200(args):
     variables, ps_tasks, placement = WORKLOADS[args.workload]
     n_full = n_params(args.workload)
 
+    wire = psx.BF16 if args.wire == "bf16" else psx.F32
+    esz = 2 if args.wire == "bf16" else 4
     cl = engine.TorchrunCluster(variables, ps_tasks, engine.AdamOptimizer(0.01),
                                 placement=placement, stripes=args.stripes,
-                                fused=(args.path == "fused"), device=local_rank)
+                                fused=(args.path == "fused"), wire=wire, device=local_rank)
     gen = torch.Generator(device="cuda").manual_seed(100 + rank)
     for t in cl.worker.grad_flat:
         t.copy_(torch.randn(t.numel(), device="cuda", generator=gen) * 1e-2)
@@ -379,7 +384,7 @@ def run_b200(args):
     timer = KernelTimer()
     ms_step, launches = timed(steps, timer=timer)
     clocks = sampler.stop() if rank == 0 else None
-    bytes_step = world * n_full * 8
+    bytes_step = world * n_full * 2 * esz       # W * N * (s_g + s_p)
     value = bytes_step / (ms_step * 1e-3) / 1e9
 
     # dominant kernel: the fused reduce+apply (or gather/apply/scatter) kernel
@@ -394,11 +399,11 @@ def run_b200(args):
     shard_elems = ((dom.spec.nelem + 1023) // 1024) * 1024 if dom is not None else 0
     k_ms = timer.mean_ms()
     if args.path == "fused":
-        per_elem = 24 + 4 * world + 4 * world      # var/m/v r+w, W gradient reads, W param writes
-        kname = "k_apply<ADAM,%s,SCATTER,PeerSrc>" % args.mode
+        per_elem = 24 + esz * world + esz * world  # var/m/v r+w, W gradient reads, W param writes
+        kname = "k_apply<ADAM,%s,SCATTER,PeerSrc<%s>>" % (args.mode, args.wire)
     else:
-        per_elem = 24 + 4 * world                  # var/m/v r+w, W landing-slot reads
-        kname = "k_apply<ADAM,%s,SlotSrc<f32>>" % args.mode
+        per_elem = 24 + esz * world                # var/m/v r+w, W landing-slot reads
+        kname = "k_apply<ADAM,%s,SlotSrc<%s>>" % (args.mode, args.wire)
     roofline = None
     if k_ms:
         # the timer brackets the launches over this rank's largest shard only
@@ -420,7 +425,7 @@ def run_b200(args):
             # the one-shot kernel is bound by this GPU's NVLink port, not by HBM:
             # per direction it carries (N-1) remote gradient stripes in + the
             # other owners' parameter stripes in (and the mirror image out)
-            nvl_bytes = 2 * (world - 1) * shard_elems * 4
+            nvl_bytes = 2 * (world - 1) * shard_elems * esz
             nvl = nvl_bytes / (k_ms * 1e-3) / 1e9
             roofline.update({"bound": "nvlink", "achieved": nvl, "peak": 770.0,
                              "frac": nvl / 770.0,
@@ -435,7 +440,8 @@ def run_b200(args):
         # the three-kernel path (push -> landing slot, reduce+apply, pull), the one
         # asynchronous / cross-process workers use; reported beside the headline
         cl = engine.TorchrunCluster(variables, ps_tasks, engine.AdamOptimizer(0.01),
-                                    placement=placement, stripes=args.stripes, device=local_rank)
+                                    placement=placement, stripes=args.stripes, wire=wire,
+                                    device=local_rank)
         for t in cl.worker.grad_flat:
             t.copy_(torch.randn(t.numel(), device="cuda", generator=gen) * 1e-2)
         for _ in range(warmup):
@@ -443,7 +449,7 @@ def run_b200(args):
         t2 = KernelTimer()
         ms_staged, l_staged = timed(max(3, steps // 2), timer=t2)
         se = ((cl.dominant.spec.nelem + 1023) // 1024) * 1024
-        per = 24 + 4 * world
+        per = 24 + esz * world
         staged = {"value": bytes_step / (ms_staged * 1e-3) / 1e9, "unit": "GB/s",
                   "ms_per_step": ms_staged, "gpu_launches": l_staged,
                   "apply_kernel": {"kernel": "k_apply<ADAM,%s,SlotSrc<f32>>" % args.mode,
@@ -459,10 +465,12 @@ def run_b200(args):
         # shards per bucket so H2D, the kernels and D2H pipeline across shards
         e2e_stripes = max(8, world)
         cl = engine.TorchrunCluster(variables, ps_tasks, engine.AdamOptimizer(0.01),
-                                    placement=placement, stripes=e2e_stripes, device=local_rank)
+                                    placement=placement, stripes=e2e_stripes, wire=wire,
+                                    device=local_rank)
         cl.staging = engine.HostStaging(cl.worker)
         for t in cl.staging.grad:
-            t.normal_(0.0, 1e-2, generator=torch.Generator().manual_seed(200 + rank))
+            t.copy_(torch.randn(t.numel(), generator=torch.Generator().manual_seed(200 + rank))
+                    * 1e-2)
         for _ in range(2):
             one_step(host=True)
         ms_e2e, _ = timed(max(3, steps // 2), host=True)
@@ -491,7 +499,8 @@ def run_b200(args):
             "metric": "ps_push_pull_GBps", "value": value, "unit": "GB/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": "f32" if args.wire == "f32" else "f32 master / bf16 wire",
+            "data": "synthetic",
             "config": workload_config(args, world, n_full),
             "steps_per_sec": 1e3 / ms_step * (world if args.mode == "async" else 1),
             "gpu_launches": launches,

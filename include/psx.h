@@ -174,8 +174,9 @@ int psx_buffer_create(int device, uint64_t nbytes, uint64_t *out_id, void **out_
 int psx_buffer_export(uint64_t id, void *out_handle);
 int psx_buffer_destroy(uint64_t id);
 
-/* Bind worker `slot`'s gradient and parameter buffers (f32, elements
- * [elem_off, elem_off + shard nelem) of each) to a shard for psx_round. */
+/* Bind worker `slot`'s gradient and parameter buffers (elements of the shard's
+ * wire dtype -- f32, or bf16 with an f32 master on the PS -- range
+ * [elem_off, elem_off + padded shard nelem) of each) to a shard for psx_round. */
 int psx_round_bind(uint64_t shard_id, int slot, const void *grad_buf_handle,
                    const void *param_buf_handle, uint64_t elem_off);
 

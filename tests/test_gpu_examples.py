@@ -135,7 +135,15 @@ def test_matrix_factorization_two_iterations_match_oracle():
         o.sgd_apply(H, dH, 0.01)
     np.testing.assert_allclose(mat_w, W, rtol=2e-3, atol=1e-4)
     np.testing.assert_allclose(mat_h, H, rtol=2e-3, atol=1e-4)
-    assert np.isfinite(loss)
+    # the reference's 1e13 penalty makes the loss overflow float32 as soon as an
+    # entry turns negative (matrix_factorization.py:10,34-36): compare with the
+    # oracle's loss rather than insisting on a finite value
+    with np.errstate(all="ignore"):
+        want_loss, _, _ = o.nmf_grads(W, H, R)
+    if np.isfinite(want_loss):
+        np.testing.assert_allclose(loss, want_loss, rtol=1e-2)
+    else:
+        assert not np.isfinite(loss)
 
 
 def test_in_graph_mnist_runs_and_learns():

@@ -472,3 +472,40 @@ def test_launch_counter_counts_this_librarys_kernels():
     finally:
         c.close()
         shard.destroy()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("mode", [psx.MODE_ASYNC_ORDERED, psx.MODE_SUM])
+def test_bf16_wire_end_to_end_f32_master(fused, mode):
+    """BASELINE config #4: workers hold bf16 gradients and bf16 parameters, the PS
+    keeps the f32 master (var, m, v).  The master equals the oracle fed with the
+    bf16-rounded gradients bit for bit; what the workers receive is exactly
+    RNE-bf16(master)."""
+    torch = _torch()
+    n, W = 50000, 3
+    variables = [("flat", (n,))]
+    cl = engine.LocalCluster(variables, 1, W, engine.AdamOptimizer(0.01), wire=psx.BF16,
+                             fused=fused)
+    ref = o.CShard(n, o.ADAM, lr=0.01)
+    rng = np.random.default_rng(13)
+    try:
+        init = rng.standard_normal(n).astype(F)
+        cl.set_variable("flat", init)
+        ref.var[:] = init
+        assert cl.workers[0].grad_flat[0].dtype == torch.bfloat16
+        for r in range(3):
+            g32 = (rng.standard_normal((W, n)) * 0.1).astype(F)
+            gb = o.f32_to_bf16(g32).reshape(W, n)
+            for w in range(W):
+                t = torch.from_numpy(gb[w].view(np.int16)).cuda().view(torch.bfloat16)
+                cl.workers[w].grad_flat[0][:n].copy_(t)
+            cl.round(mode)
+            ref.round(o.bf16_to_f32(gb).reshape(W, n), mode)
+        torch.cuda.synchronize()
+        assert_bits_equal(cl.get_variable("flat"), ref.var, "f32 master")
+        want = o.f32_to_bf16(ref.var)
+        for w in range(W):
+            got = cl.workers[w].param_flat[0][:n].view(torch.int16).cpu().numpy().view(np.uint16)
+            assert np.array_equal(got, want), "worker %d bf16 parameters" % w
+    finally:
+        cl.close()

@@ -997,8 +997,8 @@ int psx_round_bind(uint64_t shard_id, int slot, const void *grad_buf_handle,
     if (rc) return rc;
     rc = check_blob(param_buf_handle, KIND_BUFFER, &p);
     if (rc) return rc;
-    // the kernel touches nelem_pad elements of every bound buffer
-    const uint64_t need = (elem_off + s->lay.nelem_pad) * 4;
+    // the kernel touches nelem_pad elements (of the shard's wire dtype) of every bound buffer
+    const uint64_t need = (elem_off + s->lay.nelem_pad) * s->lay.wire_bytes();
     if (g.nelem < need || p.nelem < need)
         return fail(PSX_EINVAL, "bound buffers must hold %llu bytes (elem_off + padded shard), have %llu/%llu",
                     (unsigned long long)need, (unsigned long long)g.nelem, (unsigned long long)p.nelem);
@@ -1030,24 +1030,29 @@ int psx_round(uint64_t shard_id, int mode, int first_slot, int count, uint32_t w
     if (!s) return fail(PSX_EINVAL, "unknown shard id");
     int rc = check_range(first_slot, count, PSX_MAX_SLOTS);
     if (rc) return rc;
-    PeerSrc src;
-    memset(&src, 0, sizeof(src));
-    src.first = first_slot;
-    fill_mirrors(s, &src.peers);
+    PeerSet peers;
+    memset(&peers, 0, sizeof(peers));
+    fill_mirrors(s, &peers);
+    const size_t wb = s->lay.wire_bytes();
     for (int k = 0; k < count; ++k) {
         const Bound &b = s->bound[first_slot + k];
         if (!b.valid) return fail(PSX_ESTATE, "slot %d has no bound buffers (psx_round_bind)", first_slot + k);
-        src.peers.grad[first_slot + k] = (const float *)b.grad.base + b.elem_off;
+        peers.grad[first_slot + k] = b.grad.base + b.elem_off * wb;
     }
     for (int c = 0; c < PSX_MAX_SLOTS; ++c)  // every bound worker receives the new parameters
         if (s->bound[c].valid)
-            src.peers.param[src.peers.n_param++] = (float *)s->bound[c].param.base + s->bound[c].elem_off;
+            peers.param[peers.n_param++] = s->bound[c].param.base + s->bound[c].elem_off * wb;
     PSX_DEVICE(s->device);
     // slot flags exist for all PSX_MAX_SLOTS slots, whether or not the shard has
     // landing slots (psx_round needs none)
     rc = wait_slots(s, first_slot, count, wait_seq, stream);
     if (rc) return rc;
-    return launch_apply<true>(s, mode, src, count, src.peers, (cudaStream_t)stream);
+    if (s->lay.wire == PSX_F32) {
+        PeerSrc<float> src{peers, first_slot};
+        return launch_apply<true>(s, mode, src, count, peers, (cudaStream_t)stream);
+    }
+    PeerSrc<__nv_bfloat16> src{peers, first_slot};
+    return launch_apply<true>(s, mode, src, count, peers, (cudaStream_t)stream);
 }
 
 int psx_copy(int device, void *dst, const void *src, uint64_t nbytes, void *stream)

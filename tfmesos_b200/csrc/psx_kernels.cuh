@@ -45,8 +45,8 @@ struct ClientBlock {
 };
 
 struct PeerSet {                      // by-value kernel argument (PS address space)
-    const float *grad[PSX_MAX_SLOTS]; // bound worker gradient buffers (psx_round)
-    float *param[PSX_MAX_SLOTS];      // bound worker parameter buffers, compact
+    const void *grad[PSX_MAX_SLOTS];  // bound worker gradient buffers (psx_round), wire dtype
+    void *param[PSX_MAX_SLOTS];       // bound worker parameter buffers, compact, wire dtype
     unsigned int *mirror[PSX_MAX_SLOTS];  // ClientBlock::applied of each client, compact
     int n_param;
     int n_mirror;
@@ -431,15 +431,18 @@ template <typename WIRE> struct SlotSrc {            // landing slots in the sha
         return Vec4<WIRE>::load(base + (size_t)(first + s) * stride + 4 * i);
     }
 };
-struct PeerSrc {                                     // bound worker buffers (peer HBM)
+template <typename WIRE> struct PeerSrc {            // bound worker buffers (peer HBM)
     static constexpr bool kPrefetch = true;          // NVLink round trip: prefetch one iteration
+    using wire_t = WIRE;
     PeerSet peers;
     int first;
     __device__ __forceinline__ float4 load(int s, size_t i) const
     {
-        return ld_stream((const float4 *)peers.grad[first + s] + i);
+        return Vec4<WIRE>::load((const WIRE *)peers.grad[first + s] + 4 * i);
     }
 };
+template <typename SRC> struct WireOf { using type = float; };
+template <typename W> struct WireOf<PeerSrc<W>> { using type = W; };
 
 // Fused reduce + apply over a whole shard (n4 vectors).  SCATTER: also write
 // the new parameters into every bound worker parameter buffer (psx_round).
@@ -530,9 +533,10 @@ k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restric
             st_stream(mom + i, m);
             st_stream(vel + i, v);
         }
-        if (SCATTER) {
+        if (SCATTER) {   // new parameters to every bound worker, cast to the wire dtype (RNE)
+            using W = typename WireOf<SRC>::type;
             for (int s = 0; s < peers.n_param; ++s)
-                st_stream((float4 *)peers.param[s] + i, x);
+                Vec4<W>::store((W *)peers.param[s] + 4 * i, x);
         }
     }
 

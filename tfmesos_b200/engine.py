@@ -177,10 +177,15 @@ class Worker(object):
     flat parameter tensor per PS task in ITS OWN HBM (what TF keeps as the
     worker-side copies it _Recv'd / will _Send), with per-variable views."""
 
-    def __init__(self, index, topology, handles, exportable=False):
-        """handles: {(task, stripe): shard handle bytes}."""
+    def __init__(self, index, topology, handles, exportable=False, wire=psx.F32):
+        """handles: {(task, stripe): shard handle bytes}.  wire: element type of
+        this worker's gradient / parameter tensors (f32, or bf16 for BASELINE
+        config #4 -- the PS keeps f32 master copies either way)."""
         import torch
         self.index = int(index)
+        self.wire = wire
+        dtype = torch.bfloat16 if wire == psx.BF16 else torch.float32
+        esize = 2 if wire == psx.BF16 else 4
         self.topo = topology
         self.device = topology.worker_devices[self.index]
         self.layout = topology.layout
@@ -191,13 +196,13 @@ class Worker(object):
             shards = topology.shards_of(task)
             n = _round_up(sum(s.nelem for s in shards), STRIPE_ALIGN)
             if exportable:      # psx_round needs IPC-exportable staging
-                g, p = psx.Buffer(self.device, n * 4), psx.Buffer(self.device, n * 4)
+                g, p = psx.Buffer(self.device, n * esize), psx.Buffer(self.device, n * esize)
                 self.buffers.append((g, p))
-                self.grad_flat.append(g.tensor())
-                self.param_flat.append(p.tensor())
+                self.grad_flat.append(g.tensor(dtype))
+                self.param_flat.append(p.tensor(dtype))
             else:
-                self.grad_flat.append(torch.zeros(n, dtype=torch.float32, device=dev))
-                self.param_flat.append(torch.zeros(n, dtype=torch.float32, device=dev))
+                self.grad_flat.append(torch.zeros(n, dtype=dtype, device=dev))
+                self.param_flat.append(torch.zeros(n, dtype=dtype, device=dev))
         self.clients = OrderedDict()
         for s in topology.shards:
             self.clients[s.key] = psx.Client(handles[s.key], self.device, self.index)
@@ -212,19 +217,19 @@ class Worker(object):
     def buffer_handles(self):
         return [(g.export(), p.export()) for g, p in self.buffers]
 
-    def push(self, seq=0, stream=None, dtype=psx.F32):
+    def push(self, seq=0, stream=None):
         """PUSH every bucket stripe into this worker's slot on its PS GPU."""
         for s in self.topo.shards:
             g = self.grad_flat[s.task]
             self.clients[s.key].push(g.data_ptr() + s.off * g.element_size(), s.nelem, 0,
-                                     dtype, seq, stream)
+                                     self.wire, seq, stream)
 
-    def pull(self, wait_seq=0, stream=None, dtype=psx.F32):
+    def pull(self, wait_seq=0, stream=None):
         """PULL every bucket stripe from its PS GPU into the flat parameters."""
         for s in self.topo.shards:
             p = self.param_flat[s.task]
             self.clients[s.key].pull(p.data_ptr() + s.off * p.element_size(), s.nelem, 0,
-                                     dtype, wait_seq, stream)
+                                     self.wire, wait_seq, stream)
 
     def signal(self, seq, stream=None):
         for c in self.clients.values():
@@ -266,7 +271,7 @@ class LocalCluster(object):
             self.servers[spec.key] = ParameterServer(spec, optimizer, n_workers, wire,
                                                      landing_slots=not fused)
         handles = {k: ps.handle() for k, ps in self.servers.items()}
-        self.workers = [Worker(i, self.topo, handles, exportable=fused)
+        self.workers = [Worker(i, self.topo, handles, exportable=fused, wire=wire)
                         for i in range(n_workers)]
         for w in self.workers:
             for key, h in w.client_handles().items():
@@ -341,16 +346,16 @@ class HostStaging(object):
 
     def __init__(self, worker):
         import torch
-        self.grad = [torch.empty(t.numel(), dtype=torch.float32).pin_memory()
+        self.grad = [torch.empty(t.numel(), dtype=t.dtype).pin_memory()
                      for t in worker.grad_flat]
-        self.param = [torch.empty(t.numel(), dtype=torch.float32).pin_memory()
+        self.param = [torch.empty(t.numel(), dtype=t.dtype).pin_memory()
                       for t in worker.param_flat]
 
     def h2d_bytes(self):
-        return sum(t.numel() * 4 for t in self.grad)
+        return sum(t.numel() * t.element_size() for t in self.grad)
 
     def d2h_bytes(self):
-        return sum(t.numel() * 4 for t in self.param)
+        return sum(t.numel() * t.element_size() for t in self.param)
 
 
 def merge_across_ranks(mine):
@@ -398,7 +403,7 @@ class TorchrunCluster(object):
             self.servers[spec.key] = ParameterServer(spec, optimizer, self.world, wire,
                                                      landing_slots=not fused)
         handles = self._merge({k: ps.handle() for k, ps in self.servers.items()})
-        self.worker = Worker(self.rank, self.topo, handles, exportable=fused)
+        self.worker = Worker(self.rank, self.topo, handles, exportable=fused, wire=wire)
         clients = self._merge({(k, self.rank): h
                                for k, h in self.worker.client_handles().items()})
         for (key, widx), h in clients.items():
@@ -497,14 +502,14 @@ class TorchrunCluster(object):
                     ev = torch.cuda.Event()
                     ev.record(hs)
                 ws.wait_event(ev)
-                wk.clients[sp.key].push(g.data_ptr(), sp.nelem, 0, psx.F32, seq, ws)
+                wk.clients[sp.key].push(g.data_ptr(), sp.nelem, 0, wk.wire, seq, ws)
                 ps = self.servers.get(sp.key)
                 if ps is not None:
                     ps.apply(mode, seq, pss)
             if i >= 1:
                 sp = shards[i - 1]
                 p = wk.param_flat[sp.task][sp.off:sp.off + sp.nelem]
-                wk.clients[sp.key].pull(p.data_ptr(), sp.nelem, 0, psx.F32, seq, ws)
+                wk.clients[sp.key].pull(p.data_ptr(), sp.nelem, 0, wk.wire, seq, ws)
                 ev = torch.cuda.Event()
                 ev.record(ws)
                 ds.wait_event(ev)

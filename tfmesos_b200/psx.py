@@ -291,12 +291,14 @@ class Buffer(object):
 
     @property
     def __cuda_array_interface__(self):
-        return {"shape": (self.nbytes // 4,), "typestr": "<f4", "data": (self.ptr, False),
+        return {"shape": (self.nbytes // 2,), "typestr": "<i2", "data": (self.ptr, False),
                 "version": 2, "strides": None}
 
-    def tensor(self):
+    def tensor(self, dtype=None):
+        """Zero-copy torch view of the buffer (float32 unless ``dtype`` says bfloat16)."""
         import torch
-        return torch.as_tensor(self, device="cuda:%d" % self.device)
+        raw = torch.as_tensor(self, device="cuda:%d" % self.device)
+        return raw.view(torch.float32 if dtype is None else dtype)
 
 
 def copy(device, dst_ptr, src_ptr, nbytes, stream=None):

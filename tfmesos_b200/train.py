@@ -135,7 +135,7 @@ class ParameterClient(object):
             handles[spec.key] = endpoint.call(
                 self.ps_addrs[spec.task], 'create_shard', key=spec.key, nelem=spec.nelem,
                 opt=optimizer.opt, hyper=hyper, n_slots=self.n_workers, wire=wire)
-        self.worker = engine.Worker(self.index, self.topo, handles)
+        self.worker = engine.Worker(self.index, self.topo, handles, wire=wire)
         for key, h in self.worker.client_handles().items():
             endpoint.call(self.ps_addrs[key[0]], 'register_client', key=key,
                           slot=self.index, handle=h)
@@ -176,8 +176,9 @@ class ParameterClient(object):
         """PULL (Variable reads of the next sess.run)."""
         for spec in self.topo.shards:
             p = self.worker.param_flat[spec.task]
-            self.worker.clients[spec.key].pull(p.data_ptr() + spec.off * 4, spec.nelem, 0,
-                                               psx.F32, self.applied[spec.key], self.stream)
+            self.worker.clients[spec.key].pull(p.data_ptr() + spec.off * p.element_size(),
+                                               spec.nelem, 0, self.worker.wire,
+                                               self.applied[spec.key], self.stream)
         self.stream.synchronize()
 
     def minimize(self, mode=psx.MODE_ASYNC_ORDERED):
