@@ -177,3 +177,33 @@ def test_model_gradients_against_torch_autograd():
     tl.backward()
     np.testing.assert_allclose(dWm, tWm.grad.numpy(), rtol=1e-3, atol=1e-3)
     np.testing.assert_allclose(dHm, tHm.grad.numpy(), rtol=1e-3, atol=1e-3)
+
+
+def test_sgd_matches_torch_optim_sgd_and_adam_differs_from_torch_adam():
+    """plain SGD is the same algebra as torch.optim.SGD (to 1 ulp:
+    torch's CPU kernel evaluates p + (-lr)*g with a fused multiply-add, Eigen and
+    the oracle round the product first); TF-form Adam is NOT torch.optim.Adam
+    (epsilon placement), which is why torch's optimizer is never used as oracle."""
+    import torch
+    rng = np.random.default_rng(3)
+    p0 = rng.standard_normal(1000).astype(F)
+    gs = [rng.standard_normal(1000).astype(F) for _ in range(5)]
+    s = o.Shard(1000, o.SGD, lr=0.005)
+    s.var[:] = p0
+    tp = torch.tensor(p0.copy(), requires_grad=True)
+    opt = torch.optim.SGD([tp], lr=0.005)
+    for g in gs:
+        s.round(g[None, :], o.ASYNC_ORDERED)
+        tp.grad = torch.tensor(g)
+        opt.step()
+    np.testing.assert_allclose(s.var, tp.detach().numpy(), rtol=3e-7, atol=1e-9)
+    a = o.Shard(1000, o.ADAM, lr=0.01)
+    a.var[:] = p0
+    tq = torch.tensor(p0.copy(), requires_grad=True)
+    topt = torch.optim.Adam([tq], lr=0.01, betas=(0.9, 0.999), eps=1e-8)
+    for g in gs:
+        small = (g * F(1e-8)).astype(F)           # |g| ~ eps: the two conventions split
+        a.round(small[None, :], o.ASYNC_ORDERED)
+        tq.grad = torch.tensor(small)
+        topt.step()
+    assert not np.allclose(a.var, tq.detach().numpy(), rtol=1e-3, atol=0)
