@@ -509,3 +509,41 @@ def test_bf16_wire_end_to_end_f32_master(fused, mode):
             assert np.array_equal(got, want), "worker %d bf16 parameters" % w
     finally:
         cl.close()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_torchrun_cluster_single_rank_batched_and_stepwise_rounds(fused):
+    """engine.TorchrunCluster at world size 1 (what bench.py drives): a round
+    issued as ONE psx_batch call and a round issued call by call (the timed
+    variant) give the same bits as the oracle."""
+    torch = _torch()
+
+    class NullTimer(object):
+        def start(self, s):
+            pass
+
+        def stop(self, s):
+            pass
+
+    variables = [("W", (3000, 40)), ("H", (40, 500))]
+    cl = engine.TorchrunCluster(variables, 2, engine.AdamOptimizer(0.01),
+                                placement={"W": 0, "H": 1}, stripes=3, fused=fused, device=0)
+    refs = [o.CShard(cl.layout.bucket_nelem[t], o.ADAM, lr=0.01) for t in range(2)]
+    rng = np.random.default_rng(17)
+    try:
+        for r in range(4):
+            slots = []
+            for t in range(2):
+                g = (rng.standard_normal(refs[t].n) * 0.1).astype(F)
+                cl.worker.grad_flat[t][:refs[t].n].copy_(torch.from_numpy(g))
+                slots.append(g)
+            torch.cuda.synchronize()
+            cl.round(psx.MODE_SUM, NullTimer() if r % 2 else None)
+            for t in range(2):
+                refs[t].round(slots[t][None, :], o.SUM)
+        cl.barrier()
+        for t in range(2):
+            got = cl.worker.param_flat[t][:refs[t].n].cpu().numpy()
+            assert_bits_equal(got, refs[t].var, "ps task %d" % t)
+    finally:
+        cl.close()

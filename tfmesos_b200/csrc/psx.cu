@@ -1055,6 +1055,30 @@ int psx_round(uint64_t shard_id, int mode, int first_slot, int count, uint32_t w
     return launch_apply<true>(s, mode, src, count, peers, (cudaStream_t)stream);
 }
 
+int psx_batch(const psx_op *ops, int n_ops, int *failed_index)
+{
+    if (!ops || n_ops < 0) return fail(PSX_EINVAL, "bad batch");
+    for (int i = 0; i < n_ops; ++i) {
+        const psx_op &o = ops[i];
+        int rc;
+        switch (o.op) {
+        case PSX_OP_PUSH: rc = psx_push(o.id, o.ptr, o.off, o.n, o.a, o.seq, o.stream); break;
+        case PSX_OP_PULL: rc = psx_pull(o.id, o.ptr, o.off, o.n, o.a, o.seq, o.stream); break;
+        case PSX_OP_APPLY: rc = psx_apply(o.id, o.a, o.b, o.c, o.seq, o.stream); break;
+        case PSX_OP_ROUND: rc = psx_round(o.id, o.a, o.b, o.c, o.seq, o.stream); break;
+        case PSX_OP_SIGNAL: rc = psx_signal(o.id, o.seq, o.stream); break;
+        case PSX_OP_WAIT_APPLIED: rc = psx_wait_applied(o.id, o.seq, o.stream); break;
+        case PSX_OP_WAIT_SLOTS: rc = psx_wait_slots(o.id, o.b, o.c, o.seq, o.stream); break;
+        default: rc = fail(PSX_EINVAL, "batch op %d: unknown opcode %d", i, o.op);
+        }
+        if (rc) {
+            if (failed_index) *failed_index = i;
+            return rc;
+        }
+    }
+    return PSX_OK;
+}
+
 int psx_copy(int device, void *dst, const void *src, uint64_t nbytes, void *stream)
 {
     if (nbytes % 4) return fail(PSX_EINVAL, "nbytes must be a multiple of 4");

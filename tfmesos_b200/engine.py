@@ -421,6 +421,7 @@ class TorchrunCluster(object):
         self.dominant = max(self.servers.values(), key=lambda ps: ps.spec.nelem,
                             default=None)
         self.seq = 0
+        self._batches = {}
         self.staging = None
         self.h2d_stream = self.d2h_stream = None
         self.barrier()
@@ -447,16 +448,51 @@ class TorchrunCluster(object):
             if lo < hi:
                 ps.shard.set_values(psx.VAR, flat[lo - off:hi - off], lo - spec.off)
 
+    def _build_batch(self, mode):
+        """The round as one psx_batch: the same ops round() issues one by one."""
+        ws, pss, wk = self.worker_stream, self.ps_stream, self.worker
+        ops = []
+        if self.fused:
+            for c in wk.clients.values():
+                ops.append(dict(op=psx.OP_SIGNAL, id=c.id, stream=ws))
+            for ps in self.servers.values():
+                ops.append(dict(op=psx.OP_ROUND, id=ps.shard.id, a=mode, b=0, c=self.world,
+                                stream=pss))
+            for c in wk.clients.values():
+                ops.append(dict(op=psx.OP_WAIT_APPLIED, id=c.id, stream=ws))
+        else:
+            for sp in self.topo.shards:
+                g = wk.grad_flat[sp.task]
+                ops.append(dict(op=psx.OP_PUSH, id=wk.clients[sp.key].id,
+                                ptr=g.data_ptr() + sp.off * g.element_size(), off=0,
+                                n=sp.nelem, a=wk.wire, stream=ws))
+            for ps in self.servers.values():
+                ops.append(dict(op=psx.OP_APPLY, id=ps.shard.id, a=mode, b=0, c=self.world,
+                                stream=pss))
+            for sp in self.topo.shards:
+                p = wk.param_flat[sp.task]
+                ops.append(dict(op=psx.OP_PULL, id=wk.clients[sp.key].id,
+                                ptr=p.data_ptr() + sp.off * p.element_size(), off=0,
+                                n=sp.nelem, a=wk.wire, stream=ws))
+        return psx.Batch(ops)
+
     def round(self, mode, timer=None):
         """One global PS round, fully asynchronous: worker stream = push ... pull,
-        PS stream = wait(flags) + apply; the GPUs' front ends do the ordering."""
+        PS stream = wait(flags) + apply; the GPUs' front ends do the ordering.
+        Without a timer the whole round is ONE call into libpsx (psx_batch)."""
         self.seq += 1
+        if timer is None:
+            batch = self._batches.get(mode)
+            if batch is None:
+                batch = self._batches[mode] = self._build_batch(mode)
+            batch.run(self.seq)
+            return
         ws, pss = self.worker_stream, self.ps_stream
         if self.fused:
             self.worker.signal(self.seq, ws)
             for ps in self.servers.values():
                 ps.shard.wait_slots(0, self.world, self.seq, pss)
-                timed = timer is not None and ps is self.dominant
+                timed = ps is self.dominant
                 if timed:
                     timer.start(pss)
                 ps.round(mode, 0, pss)
@@ -467,7 +503,7 @@ class TorchrunCluster(object):
             self.worker.push(self.seq, ws)
             for ps in self.servers.values():
                 ps.shard.wait_slots(0, self.world, self.seq, pss)
-                timed = timer is not None and ps is self.dominant
+                timed = ps is self.dominant
                 if timed:
                     timer.start(pss)
                 ps.apply(mode, 0, pss)

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libpsx.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 OPT_SGD, OPT_ADAM = 0, 1
 MODE_ASYNC_ORDERED, MODE_SUM, MODE_SYNC_MEAN = 0, 1, 2
 F32, BF16 = 0, 1
@@ -25,6 +25,16 @@ _u32 = ctypes.c_uint32
 _i32 = ctypes.c_int
 _vp = ctypes.c_void_p
 _fp = ctypes.POINTER(ctypes.c_float)
+
+OP_PUSH, OP_PULL, OP_APPLY, OP_ROUND, OP_SIGNAL, OP_WAIT_APPLIED, OP_WAIT_SLOTS = range(1, 8)
+
+
+class Op(ctypes.Structure):
+    """struct psx_op (include/psx.h)."""
+    _fields_ = [("op", ctypes.c_int32), ("a", ctypes.c_int32), ("b", ctypes.c_int32),
+                ("c", ctypes.c_int32), ("id", _u64), ("off", _u64), ("n", _u64),
+                ("ptr", _vp), ("stream", _vp), ("seq", _u32), ("reserved", _u32)]
+
 
 # name -> (restype, argtypes); every symbol include/psx.h declares
 SIGNATURES = {
@@ -62,6 +72,7 @@ SIGNATURES = {
     "psx_signal": (_i32, [_u64, _u32, _vp]),
     "psx_wait_applied": (_i32, [_u64, _u32, _vp]),
     "psx_round": (_i32, [_u64, _i32, _i32, _i32, _u32, _vp]),
+    "psx_batch": (_i32, [ctypes.POINTER(Op), _i32, ctypes.POINTER(_i32)]),
     "psx_launch_count": (_u64, []),
     "psx_shard_ptr": (_i32, [_u64, _i32, ctypes.POINTER(_vp)]),
     "psx_copy": (_i32, [_i32, _vp, _vp, _u64, _vp]),
@@ -299,6 +310,37 @@ class Buffer(object):
         import torch
         raw = torch.as_tensor(self, device="cuda:%d" % self.device)
         return raw.view(torch.float32 if dtype is None else dtype)
+
+
+class Batch(object):
+    """A fixed sequence of ops replayed with fresh sequence numbers: one ABI
+    crossing per PS round (psx_batch)."""
+
+    def __init__(self, ops):
+        """ops: list of dicts with the psx_op field names (stream: torch stream,
+        raw pointer or None)."""
+        self.array = (Op * len(ops))()
+        self.seq_slots = []
+        for i, spec in enumerate(ops):
+            o = self.array[i]
+            for k, v in spec.items():
+                if k == "stream":
+                    v = _stream_ptr(v)
+                elif k == "uses_seq":
+                    continue
+                setattr(o, k, v)
+            if spec.get("uses_seq", True):
+                self.seq_slots.append(i)
+        self.n = len(ops)
+        self._failed = _i32(-1)
+
+    def run(self, seq):
+        for i in self.seq_slots:
+            self.array[i].seq = seq
+        rc = lib().psx_batch(self.array, self.n, ctypes.byref(self._failed))
+        if rc != 0:
+            raise RuntimeError("psx batch op %d failed (%d): %s"
+                               % (self._failed.value, rc, last_error()))
 
 
 def copy(device, dst_ptr, src_ptr, nbytes, stream=None):
