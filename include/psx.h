@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PSX_ABI_VERSION 5
+#define PSX_ABI_VERSION 6
 
 /* error codes */
 #define PSX_OK 0
@@ -185,6 +185,24 @@ int psx_round_bind(uint64_t shard_id, int slot, const void *grad_buf_handle,
 int psx_signal(uint64_t client_id, uint32_t seq, void *stream);
 int psx_wait_applied(uint64_t client_id, uint32_t seq, void *stream);
 
+/* Counter-based rendez-vous for synchronous rounds with many shards (one stream
+ * memop instead of one per slot / per shard):
+ *   - every completed psx_push / psx_signal also bumps the shard's `arrivals`
+ *     counter; psx_wait_arrivals makes the stream wait for arrivals >= target
+ *     (target = round * n_workers when every worker signals once per round);
+ *   - a worker's MAILBOX is a counter in its own HBM that every shard it is
+ *     registered with bumps when an apply / round completes; psx_wait_mailbox
+ *     waits for counter >= target (target = round * n_shards);
+ *   - psx_signal_many publishes one worker's readiness to up to 64 shards in a
+ *     single launch. */
+int psx_signal_many(const uint64_t *client_ids, int n, uint32_t seq, void *stream);
+int psx_wait_arrivals(uint64_t shard_id, uint32_t target, void *stream);
+int psx_mailbox_create(int device, uint64_t *out_id);
+int psx_mailbox_export(uint64_t id, void *out_handle);
+int psx_mailbox_destroy(uint64_t id);
+int psx_shard_register_mailbox(uint64_t shard_id, int slot, const void *mailbox_handle);
+int psx_wait_mailbox(uint64_t id, uint32_t target, void *stream);
+
 /* ONE kernel on the PS GPU: gather the bound gradients straight from the
  * workers' HBM (peer loads), reduce in registers in slot order, apply
  * SGD/Adam to var/m/v in place, and scatter the new parameters into every
@@ -207,6 +225,9 @@ int psx_round(uint64_t shard_id, int mode, int first_slot, int count, uint32_t w
 #define PSX_OP_SIGNAL 5        /* id=client seq                                      */
 #define PSX_OP_WAIT_APPLIED 6  /* id=client seq                                      */
 #define PSX_OP_WAIT_SLOTS 7    /* id=shard b=first_slot c=count seq=wait_seq         */
+#define PSX_OP_SIGNAL_MANY 8   /* ptr=uint64 client ids, n=count, seq                */
+#define PSX_OP_WAIT_ARRIVALS 9 /* id=shard, waits for arrivals >= seq * c            */
+#define PSX_OP_WAIT_MAILBOX 10 /* id=mailbox, waits for counter >= seq * c           */
 typedef struct psx_op {
     int32_t op, a, b, c;
     uint64_t id, off, n;

@@ -106,7 +106,7 @@ constexpr uint32_t kMagic = 0x50535831u;  // "PSX1"
 constexpr size_t kHeaderBytes = 4096;
 constexpr uint64_t kPadElems = 1024;      // every region starts 4 KiB aligned
 
-enum Kind : uint32_t { KIND_SHARD = 1, KIND_CLIENT = 2, KIND_BUFFER = 3 };
+enum Kind : uint32_t { KIND_SHARD = 1, KIND_CLIENT = 2, KIND_BUFFER = 3, KIND_MAILBOX = 4 };
 
 struct HandleBlob {           // PSX_HANDLE_BYTES, shipped between processes
     uint32_t magic, abi, kind;
@@ -149,6 +149,8 @@ struct Shard {
     Mapped client_map[PSX_MAX_SLOTS];
     unsigned int *mirror[PSX_MAX_SLOTS] = {};
     Bound bound[PSX_MAX_SLOTS];
+    Mapped mailbox_map[PSX_MAX_SLOTS];
+    unsigned int *mailbox[PSX_MAX_SLOTS] = {};
     ShardHeader *hdr() const { return (ShardHeader *)base; }
     float *var() const { return (float *)(base + lay.off_var()); }
     float *m() const { return (float *)(base + lay.off_m()); }
@@ -166,6 +168,11 @@ struct Client {
     ShardHeader *hdr() const { return (ShardHeader *)shard.base; }
     float *var() const { return (float *)(shard.base + lay.off_var()); }
     char *my_slot() const { return shard.base + lay.off_slots() + (size_t)slot * lay.nelem_pad * lay.wire_bytes(); }
+};
+
+struct Mailbox {              // a worker's completion counter, in ITS HBM
+    int device = 0;
+    unsigned int *counter = nullptr;
 };
 
 struct TensorList {
@@ -187,6 +194,7 @@ std::unordered_map<uint64_t, Shard *> g_shards;
 std::unordered_map<uint64_t, Client *> g_clients;
 std::unordered_map<uint64_t, Buffer *> g_buffers;
 std::unordered_map<uint64_t, TensorList *> g_lists;
+std::unordered_map<uint64_t, Mailbox *> g_mailboxes;
 std::atomic<uint64_t> g_next_id{1};
 std::atomic<uint64_t> g_launches{0};
 
@@ -219,6 +227,9 @@ int open_blob(const HandleBlob &b, int device, Mapped *out)
         } else if (b.kind == KIND_BUFFER) {
             auto it = g_buffers.find(b.local_id);
             if (it != g_buffers.end()) base = it->second->base;
+        } else if (b.kind == KIND_MAILBOX) {
+            auto it = g_mailboxes.find(b.local_id);
+            if (it != g_mailboxes.end()) base = (char *)it->second->counter;
         }
         if (!base) return fail(PSX_EINVAL, "handle refers to an object this process no longer has");
         out->base = base;
@@ -286,7 +297,8 @@ inline int grid_for(size_t work_items, int threads, int sm_count, int ctas_per_s
 
 // dst/src element types resolved at run time -> the four k_copy instances
 int launch_copy(void *dst, int dst_t, const void *src, int src_t, uint64_t n, int sm_count,
-                unsigned int *ticket, unsigned int *flag, uint32_t seq, cudaStream_t st)
+                unsigned int *ticket, unsigned int *flag, uint32_t seq, cudaStream_t st,
+                unsigned int *arrivals = nullptr)
 {
     if (n == 0 && flag == nullptr) return PSX_OK;
     const size_t sb = src_t == PSX_BF16 ? 2 : 4, db = dst_t == PSX_BF16 ? 2 : 4;
@@ -296,7 +308,7 @@ int launch_copy(void *dst, int dst_t, const void *src, int src_t, uint64_t n, in
     const int grid = grid_for(items ? items : 1, kCopyThreads, sm_count, 8);
 #define PSX_COPY(S, D)                                                                        \
     k_copy<S, D><<<grid, kCopyThreads, 0, st>>>((D *)dst, (const S *)src, (size_t)n, vec_ok, \
-                                                 ticket, flag, seq)
+                                                 ticket, flag, arrivals, seq)
     if (src_t == PSX_F32 && dst_t == PSX_F32) PSX_COPY(float, float);
     else if (src_t == PSX_F32 && dst_t == PSX_BF16) PSX_COPY(float, __nv_bfloat16);
     else if (src_t == PSX_BF16 && dst_t == PSX_F32) PSX_COPY(__nv_bfloat16, float);
@@ -337,8 +349,11 @@ void fill_mirrors(Shard *s, PeerSet *p)
 {
     p->n_mirror = 0;
     p->n_param = 0;
-    for (int c = 0; c < PSX_MAX_SLOTS; ++c)
+    p->n_mailbox = 0;
+    for (int c = 0; c < PSX_MAX_SLOTS; ++c) {
         if (s->mirror[c]) p->mirror[p->n_mirror++] = s->mirror[c];
+        if (s->mailbox[c]) p->mailbox[p->n_mailbox++] = s->mailbox[c];
+    }
 }
 
 int wait_slots(Shard *s, int first, int count, uint32_t wait_seq, void *stream)
@@ -464,6 +479,7 @@ int psx_shard_destroy(uint64_t id)
     cudaDeviceSynchronize();
     for (int c = 0; c < PSX_MAX_SLOTS; ++c) {
         close_mapped(s->client_map[c]);
+        close_mapped(s->mailbox_map[c]);
         close_mapped(s->bound[c].grad);
         close_mapped(s->bound[c].param);
     }
@@ -758,7 +774,7 @@ int psx_push(uint64_t client_id, const void *grad_dev, uint64_t off, uint64_t n,
     char *dst = c->my_slot() + off * c->lay.wire_bytes();
     unsigned int *flag = seq ? &c->hdr()->slot_seq[c->slot] : nullptr;
     return launch_copy(dst, c->lay.wire, grad_dev, src_dtype, n, c->sm_count, &c->block->ticket,
-                       flag, seq, (cudaStream_t)stream);
+                       flag, seq, (cudaStream_t)stream, seq ? &c->hdr()->arrivals : nullptr);
 }
 
 int psx_pull(uint64_t client_id, void *param_dev, uint64_t off, uint64_t n, int out_dtype,
@@ -778,14 +794,121 @@ int psx_pull(uint64_t client_id, void *param_dev, uint64_t off, uint64_t n, int 
                        nullptr, 0, (cudaStream_t)stream);
 }
 
-int psx_signal(uint64_t client_id, uint32_t seq, void *stream)
+int psx_signal_many(const uint64_t *client_ids, int n, uint32_t seq, void *stream)
 {
-    Client *c = find(g_clients, client_id);
-    if (!c) return fail(PSX_EINVAL, "unknown client id");
-    PSX_DEVICE(c->device);
-    k_signal<<<1, 1, 0, (cudaStream_t)stream>>>(&c->hdr()->slot_seq[c->slot], seq);
+    if (!client_ids || n < 1 || n > kMaxSignal)
+        return fail(PSX_EINVAL, "psx_signal_many takes 1..%d clients", kMaxSignal);
+    SignalSet set;
+    memset(&set, 0, sizeof(set));
+    set.n = n;
+    int device = -1;
+    for (int i = 0; i < n; ++i) {
+        Client *c = find(g_clients, client_ids[i]);
+        if (!c) return fail(PSX_EINVAL, "unknown client id (entry %d)", i);
+        if (device < 0) device = c->device;
+        if (c->device != device) return fail(PSX_EINVAL, "clients of one signal must share a device");
+        set.flag[i] = &c->hdr()->slot_seq[c->slot];
+        set.arrivals[i] = &c->hdr()->arrivals;
+    }
+    PSX_DEVICE(device);
+    k_signal<<<1, kMaxSignal, 0, (cudaStream_t)stream>>>(set, seq);
     LAUNCH_CHECK();
     return PSX_OK;
+}
+
+int psx_signal(uint64_t client_id, uint32_t seq, void *stream)
+{
+    return psx_signal_many(&client_id, 1, seq, stream);
+}
+
+int psx_wait_arrivals(uint64_t shard_id, uint32_t target, void *stream)
+{
+    Shard *s = find(g_shards, shard_id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    PSX_DEVICE(s->device);
+    return stream_wait_geq(stream, &s->hdr()->arrivals, target);
+}
+
+int psx_mailbox_create(int device, uint64_t *out_id)
+{
+    if (!out_id) return fail(PSX_EINVAL, "null out id");
+    PSX_DEVICE(device);
+    void *p = nullptr;
+    CU_TRY(cudaMalloc(&p, 256));
+    CU_TRY(cudaMemset(p, 0, 256));
+    Mailbox *m = new Mailbox();
+    m->device = device;
+    m->counter = (unsigned int *)p;
+    uint64_t id = g_next_id.fetch_add(1);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_mailboxes[id] = m;
+    }
+    *out_id = id;
+    return PSX_OK;
+}
+
+int psx_mailbox_export(uint64_t id, void *out_handle)
+{
+    Mailbox *m = find(g_mailboxes, id);
+    if (!m || !out_handle) return fail(PSX_EINVAL, "unknown mailbox id or null handle");
+    HandleBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = kMagic;
+    b.abi = PSX_ABI_VERSION;
+    b.kind = KIND_MAILBOX;
+    b.device = m->device;
+    b.pid = (uint64_t)getpid();
+    b.local_id = id;
+    PSX_DEVICE(m->device);
+    CU_TRY(cudaIpcGetMemHandle(&b.ipc, m->counter));
+    memcpy(out_handle, &b, sizeof(b));
+    return PSX_OK;
+}
+
+int psx_mailbox_destroy(uint64_t id)
+{
+    Mailbox *m = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_mailboxes.find(id);
+        if (it == g_mailboxes.end()) return fail(PSX_EINVAL, "unknown mailbox id");
+        m = it->second;
+        g_mailboxes.erase(it);
+    }
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    cudaFree(m->counter);
+    delete m;
+    return PSX_OK;
+}
+
+int psx_shard_register_mailbox(uint64_t shard_id, int slot, const void *mailbox_handle)
+{
+    Shard *s = find(g_shards, shard_id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    if (slot < 0 || slot >= PSX_MAX_SLOTS) return fail(PSX_EINVAL, "slot %d out of range", slot);
+    HandleBlob b;
+    int rc = check_blob(mailbox_handle, KIND_MAILBOX, &b);
+    if (rc) return rc;
+    if (s->mailbox[slot]) {
+        close_mapped(s->mailbox_map[slot]);
+        s->mailbox[slot] = nullptr;
+    }
+    rc = enable_peer(s->device, b.device);
+    if (rc) return rc;
+    rc = open_blob(b, s->device, &s->mailbox_map[slot]);
+    if (rc) return rc;
+    s->mailbox[slot] = (unsigned int *)s->mailbox_map[slot].base;
+    return PSX_OK;
+}
+
+int psx_wait_mailbox(uint64_t id, uint32_t target, void *stream)
+{
+    Mailbox *m = find(g_mailboxes, id);
+    if (!m) return fail(PSX_EINVAL, "unknown mailbox id");
+    PSX_DEVICE(m->device);
+    return stream_wait_geq(stream, m->counter, target);
 }
 
 int psx_wait_applied(uint64_t client_id, uint32_t seq, void *stream)
@@ -880,17 +1003,18 @@ int psx_list_destroy(uint64_t list_id)
 static int launch_list(TensorList *l, Client *c, int to_shard, int use_tma, unsigned int *flag,
                        uint32_t seq, cudaStream_t st)
 {
+    unsigned int *arrivals = flag ? &c->hdr()->arrivals : nullptr;
     char *base = to_shard ? c->my_slot() : (char *)c->var();
     unsigned int *ticket = &c->block->ticket;
     if (use_tma) {
         // 64 KiB of shared memory per CTA -> 3 CTAs per SM
         int grid = l->n_chunks < l->sm_count * 3 ? l->n_chunks : l->sm_count * 3;
         k_list_tma<<<grid, kListThreads, kListStages * kListChunkBytes, st>>>(
-            l->d_chunks, l->n_chunks, base, to_shard, ticket, flag, seq);
+            l->d_chunks, l->n_chunks, base, to_shard, ticket, flag, arrivals, seq);
     } else {
         int grid = l->n_chunks < l->sm_count * 16 ? l->n_chunks : l->sm_count * 16;
         k_list_ldst<<<grid, kListThreads, 0, st>>>(l->d_chunks, l->n_chunks, base, to_shard, ticket,
-                                                    flag, seq);
+                                                    flag, arrivals, seq);
     }
     LAUNCH_CHECK();
     return PSX_OK;
@@ -1069,6 +1193,9 @@ int psx_batch(const psx_op *ops, int n_ops, int *failed_index)
         case PSX_OP_SIGNAL: rc = psx_signal(o.id, o.seq, o.stream); break;
         case PSX_OP_WAIT_APPLIED: rc = psx_wait_applied(o.id, o.seq, o.stream); break;
         case PSX_OP_WAIT_SLOTS: rc = psx_wait_slots(o.id, o.b, o.c, o.seq, o.stream); break;
+        case PSX_OP_SIGNAL_MANY: rc = psx_signal_many((const uint64_t *)o.ptr, (int)o.n, o.seq, o.stream); break;
+        case PSX_OP_WAIT_ARRIVALS: rc = psx_wait_arrivals(o.id, o.seq * (uint32_t)o.c, o.stream); break;
+        case PSX_OP_WAIT_MAILBOX: rc = psx_wait_mailbox(o.id, o.seq * (uint32_t)o.c, o.stream); break;
         default: rc = fail(PSX_EINVAL, "batch op %d: unknown opcode %d", i, o.op);
         }
         if (rc) {

@@ -33,6 +33,8 @@ struct ShardHeader {
     unsigned int ticket;              // last-CTA counter of the apply kernels
     unsigned int apply_seq;           // completed apply rounds
     unsigned int slot_seq[PSX_MAX_SLOTS];  // round number last pushed into slot s
+    unsigned int arrivals;            // +1 per completed push / signal (any slot): lets the
+                                      // PS wait for "all W workers of round r" with ONE memop
 };
 static_assert(sizeof(ShardHeader) <= 4096, "header must fit its page");
 
@@ -48,14 +50,20 @@ struct PeerSet {                      // by-value kernel argument (PS address sp
     const void *grad[PSX_MAX_SLOTS];  // bound worker gradient buffers (psx_round), wire dtype
     void *param[PSX_MAX_SLOTS];       // bound worker parameter buffers, compact, wire dtype
     unsigned int *mirror[PSX_MAX_SLOTS];  // ClientBlock::applied of each client, compact
+    unsigned int *mailbox[PSX_MAX_SLOTS]; // per-worker completion counters, compact
     int n_param;
     int n_mirror;
+    int n_mailbox;
 };
 
 // ------------------------------------------------------------ primitives ----
 __device__ __forceinline__ void st_release_sys(unsigned int *p, unsigned int v)
 {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_release_sys(unsigned int *p, unsigned int v)
+{
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // streaming (read-once) 128-bit load; works on local and peer-mapped addresses
@@ -153,7 +161,7 @@ constexpr int kCopyUnroll = 4;
 template <typename SRC, typename DST>
 __global__ void __launch_bounds__(kCopyThreads)
 k_copy(DST *__restrict__ dst, const SRC *__restrict__ src, size_t n, int vec_ok,
-       unsigned int *ticket, unsigned int *flag, unsigned int seq)
+       unsigned int *ticket, unsigned int *flag, unsigned int *arrivals, unsigned int seq)
 {
     if (vec_ok) {
         const size_t n4 = n >> 2;
@@ -188,6 +196,7 @@ k_copy(DST *__restrict__ dst, const SRC *__restrict__ src, size_t n, int vec_ok,
             *ticket = 0;
             __threadfence_system();
             st_release_sys(flag, seq);
+            if (arrivals != nullptr) red_add_release_sys(arrivals, 1u);
         }
     }
 }
@@ -258,7 +267,7 @@ __device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, u
 // to_shard = 1: PUSH (tensor -> shard_base + off), 0: PULL (shard_base + off -> tensor)
 __global__ void __launch_bounds__(kListThreads)
 k_list_tma(const ListChunk *__restrict__ chunks, int n_chunks, char *shard_base, int to_shard,
-           unsigned int *ticket, unsigned int *flag, unsigned int seq)
+           unsigned int *ticket, unsigned int *flag, unsigned int *arrivals, unsigned int seq)
 {
     extern __shared__ __align__(128) unsigned char ring[];
     __shared__ __align__(8) uint64_t full[kListStages];
@@ -318,6 +327,7 @@ k_list_tma(const ListChunk *__restrict__ chunks, int n_chunks, char *shard_base,
             *ticket = 0;
             __threadfence_system();
             st_release_sys(flag, seq);
+            if (arrivals != nullptr) red_add_release_sys(arrivals, 1u);
         }
     }
 }
@@ -325,7 +335,7 @@ k_list_tma(const ListChunk *__restrict__ chunks, int n_chunks, char *shard_base,
 // same table, plain 128-bit loads/stores (the non-TMA baseline of the list path)
 __global__ void __launch_bounds__(kListThreads)
 k_list_ldst(const ListChunk *__restrict__ chunks, int n_chunks, char *shard_base, int to_shard,
-            unsigned int *ticket, unsigned int *flag, unsigned int seq)
+            unsigned int *ticket, unsigned int *flag, unsigned int *arrivals, unsigned int seq)
 {
     for (int j = blockIdx.x; j < n_chunks; j += gridDim.x) {
         const ListChunk c = chunks[j];
@@ -352,15 +362,26 @@ k_list_ldst(const ListChunk *__restrict__ chunks, int n_chunks, char *shard_base
             *ticket = 0;
             __threadfence_system();
             st_release_sys(flag, seq);
+            if (arrivals != nullptr) red_add_release_sys(arrivals, 1u);
         }
     }
 }
 
-// one thread: release-store a flag (psx_signal)
-__global__ void k_signal(unsigned int *flag, unsigned int seq)
+// "my gradients for round seq are in place", to up to kMaxSignal shards in ONE
+// launch: thread i publishes slot flag i and bumps that shard's arrival counter
+constexpr int kMaxSignal = 64;
+struct SignalSet {
+    unsigned int *flag[kMaxSignal];
+    unsigned int *arrivals[kMaxSignal];
+    int n;
+};
+__global__ void k_signal(SignalSet set, unsigned int seq)
 {
-    __threadfence_system();
-    st_release_sys(flag, seq);
+    if ((int)threadIdx.x < set.n) {
+        __threadfence_system();
+        st_release_sys(set.flag[threadIdx.x], seq);
+        red_add_release_sys(set.arrivals[threadIdx.x], 1u);
+    }
 }
 
 // --------------------------------------------------------------- optimizer ---
@@ -557,6 +578,7 @@ k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restric
         __threadfence_system();
         st_release_sys(&h->apply_seq, seq);
         for (int c = 0; c < peers.n_mirror; ++c) st_release_sys(peers.mirror[c], seq);
+        for (int c = 0; c < peers.n_mailbox; ++c) red_add_release_sys(peers.mailbox[c], 1u);
     }
 }
 

@@ -409,6 +409,13 @@ class TorchrunCluster(object):
         for (key, widx), h in clients.items():
             if key in self.servers:
                 self.servers[key].shard.register_client(widx, h)
+        # counter rendez-vous: one mailbox per worker, bumped by every shard's apply
+        self.mailbox = psx.Mailbox(self.device)
+        boxes = self._merge({self.rank: self.mailbox.export()})
+        for ps in self.servers.values():
+            for widx, h in boxes.items():
+                ps.shard.register_mailbox(widx, h)
+        self.n_shards = len(self.topo.shards)
         if fused:
             bufs = self._merge({self.rank: self.worker.buffer_handles()})
             for key, ps in self.servers.items():
@@ -450,36 +457,43 @@ class TorchrunCluster(object):
 
     def _build_batch(self, mode):
         """The round as one psx_batch: the same ops round() issues one by one."""
+        import ctypes
         ws, pss, wk = self.worker_stream, self.ps_stream, self.worker
         ops = []
+        keep = []
         if self.fused:
-            for c in wk.clients.values():
-                ops.append(dict(op=psx.OP_SIGNAL, id=c.id, stream=ws))
-            for ps in self.servers.values():
-                ops.append(dict(op=psx.OP_ROUND, id=ps.shard.id, a=mode, b=0, c=self.world,
-                                stream=pss))
-            for c in wk.clients.values():
-                ops.append(dict(op=psx.OP_WAIT_APPLIED, id=c.id, stream=ws))
+            ids = (ctypes.c_uint64 * len(wk.clients))(*[c.id for c in wk.clients.values()])
+            keep.append(ids)
+            ops.append(dict(op=psx.OP_SIGNAL_MANY, ptr=ctypes.addressof(ids), n=len(ids),
+                            stream=ws))
         else:
             for sp in self.topo.shards:
                 g = wk.grad_flat[sp.task]
                 ops.append(dict(op=psx.OP_PUSH, id=wk.clients[sp.key].id,
                                 ptr=g.data_ptr() + sp.off * g.element_size(), off=0,
                                 n=sp.nelem, a=wk.wire, stream=ws))
-            for ps in self.servers.values():
-                ops.append(dict(op=psx.OP_APPLY, id=ps.shard.id, a=mode, b=0, c=self.world,
-                                stream=pss))
+        for ps in self.servers.values():
+            ops.append(dict(op=psx.OP_WAIT_ARRIVALS, id=ps.shard.id, c=self.world, stream=pss))
+            ops.append(dict(op=psx.OP_ROUND if self.fused else psx.OP_APPLY, id=ps.shard.id,
+                            a=mode, b=0, c=self.world, stream=pss, uses_seq=False))
+        ops.append(dict(op=psx.OP_WAIT_MAILBOX, id=self.mailbox.id, c=self.n_shards, stream=ws))
+        if not self.fused:
             for sp in self.topo.shards:
                 p = wk.param_flat[sp.task]
                 ops.append(dict(op=psx.OP_PULL, id=wk.clients[sp.key].id,
                                 ptr=p.data_ptr() + sp.off * p.element_size(), off=0,
-                                n=sp.nelem, a=wk.wire, stream=ws))
-        return psx.Batch(ops)
+                                n=sp.nelem, a=wk.wire, stream=ws, uses_seq=False))
+        batch = psx.Batch(ops)
+        batch.keep = keep
+        return batch
 
     def round(self, mode, timer=None):
-        """One global PS round, fully asynchronous: worker stream = push ... pull,
-        PS stream = wait(flags) + apply; the GPUs' front ends do the ordering.
-        Without a timer the whole round is ONE call into libpsx (psx_batch)."""
+        """One global PS round, fully asynchronous: worker stream = signal/push ...
+        wait/pull, PS stream = wait(arrival counter) + kernel; the GPUs' front
+        ends do the ordering.  Synchronisation cost per rank and round is constant
+        in the number of shards: one signal launch (fused) and one stream wait
+        per hosted shard plus one on the worker's mailbox.  Without a timer the
+        whole round is ONE call into libpsx (psx_batch)."""
         self.seq += 1
         if timer is None:
             batch = self._batches.get(mode)
@@ -487,29 +501,25 @@ class TorchrunCluster(object):
                 batch = self._batches[mode] = self._build_batch(mode)
             batch.run(self.seq)
             return
-        ws, pss = self.worker_stream, self.ps_stream
+        ws, pss, wk = self.worker_stream, self.ps_stream, self.worker
         if self.fused:
-            self.worker.signal(self.seq, ws)
-            for ps in self.servers.values():
-                ps.shard.wait_slots(0, self.world, self.seq, pss)
-                timed = ps is self.dominant
-                if timed:
-                    timer.start(pss)
-                ps.round(mode, 0, pss)
-                if timed:
-                    timer.stop(pss)
-            self.worker.wait_applied(self.seq, ws)
+            psx.signal_many(list(wk.clients.values()), self.seq, ws)
         else:
-            self.worker.push(self.seq, ws)
-            for ps in self.servers.values():
-                ps.shard.wait_slots(0, self.world, self.seq, pss)
-                timed = ps is self.dominant
-                if timed:
-                    timer.start(pss)
+            wk.push(self.seq, ws)
+        for ps in self.servers.values():
+            ps.shard.wait_arrivals(self.seq * self.world, pss)
+            timed = ps is self.dominant
+            if timed:
+                timer.start(pss)
+            if self.fused:
+                ps.round(mode, 0, pss)
+            else:
                 ps.apply(mode, 0, pss)
-                if timed:
-                    timer.stop(pss)
-            self.worker.pull(self.seq, ws)
+            if timed:
+                timer.stop(pss)
+        self.mailbox.wait(self.seq * self.n_shards, ws)
+        if not self.fused:
+            wk.pull(0, ws)
 
     def round_host(self, mode):
         """The same round from HOST buffers, software-pipelined over the shards:
@@ -541,7 +551,8 @@ class TorchrunCluster(object):
                 wk.clients[sp.key].push(g.data_ptr(), sp.nelem, 0, wk.wire, seq, ws)
                 ps = self.servers.get(sp.key)
                 if ps is not None:
-                    ps.apply(mode, seq, pss)
+                    ps.shard.wait_arrivals(seq * self.world, pss)
+                    ps.apply(mode, 0, pss)
             if i >= 1:
                 sp = shards[i - 1]
                 p = wk.param_flat[sp.task][sp.off:sp.off + sp.nelem]
@@ -555,11 +566,13 @@ class TorchrunCluster(object):
 
     def close(self):
         self.barrier()
+        self._batches.clear()
         self.worker.close()
         self.barrier()
         for ps in self.servers.values():
             ps.close()
         self.servers.clear()
+        self.mailbox.destroy()
 
 
 class TensorListBinding(object):

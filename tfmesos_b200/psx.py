@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libpsx.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 OPT_SGD, OPT_ADAM = 0, 1
 MODE_ASYNC_ORDERED, MODE_SUM, MODE_SYNC_MEAN = 0, 1, 2
 F32, BF16 = 0, 1
@@ -26,7 +26,8 @@ _i32 = ctypes.c_int
 _vp = ctypes.c_void_p
 _fp = ctypes.POINTER(ctypes.c_float)
 
-OP_PUSH, OP_PULL, OP_APPLY, OP_ROUND, OP_SIGNAL, OP_WAIT_APPLIED, OP_WAIT_SLOTS = range(1, 8)
+(OP_PUSH, OP_PULL, OP_APPLY, OP_ROUND, OP_SIGNAL, OP_WAIT_APPLIED, OP_WAIT_SLOTS,
+ OP_SIGNAL_MANY, OP_WAIT_ARRIVALS, OP_WAIT_MAILBOX) = range(1, 11)
 
 
 class Op(ctypes.Structure):
@@ -72,6 +73,13 @@ SIGNATURES = {
     "psx_signal": (_i32, [_u64, _u32, _vp]),
     "psx_wait_applied": (_i32, [_u64, _u32, _vp]),
     "psx_round": (_i32, [_u64, _i32, _i32, _i32, _u32, _vp]),
+    "psx_signal_many": (_i32, [ctypes.POINTER(_u64), _i32, _u32, _vp]),
+    "psx_wait_arrivals": (_i32, [_u64, _u32, _vp]),
+    "psx_mailbox_create": (_i32, [_i32, ctypes.POINTER(_u64)]),
+    "psx_mailbox_export": (_i32, [_u64, _vp]),
+    "psx_mailbox_destroy": (_i32, [_u64]),
+    "psx_shard_register_mailbox": (_i32, [_u64, _i32, _vp]),
+    "psx_wait_mailbox": (_i32, [_u64, _u32, _vp]),
     "psx_batch": (_i32, [ctypes.POINTER(Op), _i32, ctypes.POINTER(_i32)]),
     "psx_launch_count": (_u64, []),
     "psx_shard_ptr": (_i32, [_u64, _i32, ctypes.POINTER(_vp)]),
@@ -201,6 +209,12 @@ class Shard(object):
     def register_client(self, slot, client_handle):
         _check(lib().psx_shard_register_client(self.id, int(slot), client_handle))
 
+    def register_mailbox(self, slot, mailbox_handle):
+        _check(lib().psx_shard_register_mailbox(self.id, int(slot), mailbox_handle))
+
+    def wait_arrivals(self, target, stream=None):
+        _check(lib().psx_wait_arrivals(self.id, int(target) & 0xFFFFFFFF, _stream_ptr(stream)))
+
     def apply(self, mode, first_slot=0, count=1, wait_seq=0, stream=None):
         _check(lib().psx_apply(self.id, int(mode), int(first_slot), int(count),
                                int(wait_seq), _stream_ptr(stream)))
@@ -251,6 +265,35 @@ class Client(object):
 
     def wait_applied(self, seq, stream=None):
         _check(lib().psx_wait_applied(self.id, int(seq), _stream_ptr(stream)))
+
+
+class Mailbox(object):
+    """A worker's completion counter in its own HBM (psx_mailbox_create): every
+    shard it is registered with bumps it when an apply / round completes."""
+
+    def __init__(self, device):
+        mid = _u64(0)
+        _check(lib().psx_mailbox_create(int(device), ctypes.byref(mid)))
+        self.id = mid.value
+        self.device = int(device)
+
+    def export(self):
+        buf = ctypes.create_string_buffer(HANDLE_BYTES)
+        _check(lib().psx_mailbox_export(self.id, buf))
+        return buf.raw
+
+    def wait(self, target, stream=None):
+        _check(lib().psx_wait_mailbox(self.id, int(target) & 0xFFFFFFFF, _stream_ptr(stream)))
+
+    def destroy(self):
+        if self.id:
+            _check(lib().psx_mailbox_destroy(self.id))
+            self.id = 0
+
+
+def signal_many(clients, seq, stream=None):
+    ids = (_u64 * len(clients))(*[c.id for c in clients])
+    _check(lib().psx_signal_many(ids, len(clients), int(seq), _stream_ptr(stream)))
 
 
 class TensorList(object):
