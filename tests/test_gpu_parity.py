@@ -547,3 +547,40 @@ def test_torchrun_cluster_single_rank_batched_and_stepwise_rounds(fused):
             assert_bits_equal(got, refs[t].var, "ps task %d" % t)
     finally:
         cl.close()
+
+
+def test_shard_larger_than_2_pow_31_elements():
+    """Maximum sizes: a shard of 2^31 + 4099 elements (8.6 GB per region) -- every
+    index computation is 64-bit.  SGD, one worker, one round, checked against the
+    oracle over the WHOLE range in 256 Mi-element windows (elementwise update, so
+    windows are independent), including the window that straddles 2^31."""
+    torch = _torch()
+    n = (1 << 31) + 4099
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * (1 << 30):
+        pytest.skip("needs ~35 GB of free HBM")
+    lr = 0.5
+    shard = psx.Shard(0, n, psx.OPT_SGD, lr=lr, n_slots=1)
+    c = psx.Client(shard.export(), 0, 0)
+    try:
+        gen = torch.Generator(device="cuda").manual_seed(31)
+        init = torch.randn(n, device="cuda", generator=gen)
+        grad = torch.randn(n, device="cuda", generator=gen)
+        psx.copy(0, shard.ptr(psx.VAR), init.data_ptr(), n * 4)
+        c.push(grad.data_ptr(), n, seq=1)
+        shard.apply(psx.MODE_SUM, 0, 1, wait_seq=1)
+        torch.cuda.synchronize()
+        lib = o.c_lib()
+        win = 1 << 28
+        for lo in range(0, n, win):
+            cnt = min(win, n - lo)
+            want = init[lo:lo + cnt].cpu().numpy()
+            g = grad[lo:lo + cnt].cpu().numpy()
+            lib.psx_oracle_sgd(want.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                               g.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), cnt, lr)
+            got = shard.get_values(psx.VAR, lo, cnt)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), "window at %d" % lo
+        assert shard.state()["global_step"] == 1
+    finally:
+        c.close()
+        shard.destroy()
