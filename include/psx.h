@@ -22,6 +22,14 @@
  * (torch.Tensor.data_ptr()); streams are cudaStream_t passed as void*
  * (torch.cuda.current_stream().cuda_stream); 0 = the legacy default stream.
  *
+ * Threading / lifetime contract: the id tables are mutex-protected, so calls on
+ * DIFFERENT ids may come from different threads (the in-graph example drives N
+ * workers from N threads, examples/mnist/mnist.py:76-80).  Calls on the same id
+ * must be ordered by the caller (normally by issuing them on one stream), and an
+ * object must outlive every other object mapped from its handle in the same
+ * process (destroy clients before the shard they opened).  No entry point
+ * synchronises the host except the *_values / *_state accessors and destroy.
+ *
  * There is no CPU fallback: without a CUDA device every compute entry point
  * fails with PSX_ECUDA.
  */

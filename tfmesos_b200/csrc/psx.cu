@@ -688,8 +688,9 @@ int psx_shard_open(const void *handle, int device, int slot, uint64_t *out_id)
     HandleBlob b;
     int rc = check_blob(handle, KIND_SHARD, &b);
     if (rc) return rc;
-    if (slot < 0 || (b.n_slots > 0 && slot >= b.n_slots))
-        return fail(PSX_EINVAL, "slot %d outside the shard's %d slots", slot, b.n_slots);
+    if (slot < 0 || slot >= PSX_MAX_SLOTS || (b.n_slots > 0 && slot >= b.n_slots))
+        return fail(PSX_EINVAL, "slot %d outside the shard's %d slots", slot,
+                    b.n_slots > 0 ? b.n_slots : PSX_MAX_SLOTS);
     rc = enable_peer(device, b.device);
     if (rc) return rc;
     Client *c = new Client();
