@@ -462,7 +462,7 @@ def run_b200(args):
     if not args.no_e2e:
         # same workload through the host-in / host-out public call; more, smaller
         # shards per bucket so H2D, the kernels and D2H pipeline across shards
-        e2e_stripes = max(8, world)
+        e2e_stripes = max(16, world)
         cl = engine.TorchrunCluster(variables, ps_tasks, engine.AdamOptimizer(0.01),
                                     placement=placement, stripes=e2e_stripes, wire=wire,
                                     device=local_rank)
