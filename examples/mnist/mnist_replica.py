@@ -122,7 +122,7 @@ def main(argv):
         grads = torch.autograd.grad(loss, ps)
         for k, g in zip(names, grads):
             sess.grads[k].copy_(g)
-        step = sess.minimize(mode)
+        step = sess.minimize(mode, FLAGS.replicas_to_aggregate if FLAGS.sync_replicas else None)
         local_step += 1
         if is_chief:
             print("%f: Worker %d: training step %d done (global step: %d)"

@@ -76,3 +76,66 @@ def test_restore_rejects_a_different_layout(tmp_path):
             checkpoint.restore(b, path)
     finally:
         b.close()
+
+
+def test_parameter_client_save_restore_through_endpoints(tmp_path):
+    """The chief checkpoints the PS tasks through their endpoints and a fresh
+    cluster restores them (Supervisor logdir stand-in)."""
+    import threading
+
+    import torch
+
+    from tfmesos_b200 import train as tf
+
+    def start(ports):
+        spec = {"ps": ["127.0.0.1:%d" % p for p in ports], "worker": ["127.0.0.1:1"]}
+        servers = [tf.Server(spec, "ps", i) for i in range(len(ports))]
+        for s in servers:
+            t = threading.Thread(target=s.join)
+            t.daemon = True
+            t.start()
+        return spec, servers
+
+    import socket
+
+    def free_ports(n):
+        socks = [socket.socket() for _ in range(n)]
+        for s in socks:
+            s.bind(("127.0.0.1", 0))
+        ports = [s.getsockname()[1] for s in socks]
+        for s in socks:
+            s.close()
+        return ports
+
+    variables = [("global_step", ()), ("w", (300, 20)), ("b", (20,))]
+    path = str(tmp_path / "model")
+    spec, servers = start(free_ports(2))
+    try:
+        sess = tf.ParameterClient(spec, variables, tf.AdamOptimizer(0.01), 0, device=0,
+                                  init={"w": np.ones((300, 20), F)})
+        for k in range(3):
+            sess.grads["w"].fill_(0.5 + k)
+            sess.grads["b"].fill_(-1.0)
+            sess.minimize()
+        files = sess.save(path)
+        assert len(files) == 2
+        want = {k: sess.read(k) for k in ("w", "b")}
+        step = sess.global_step()
+        sess.close()
+    finally:
+        for s in servers:
+            s.endpoint.stop_event.set()
+    spec2, servers2 = start(free_ports(2))
+    try:
+        sess2 = tf.ParameterClient(spec2, variables, tf.AdamOptimizer(0.01), 0, device=0)
+        assert not np.array_equal(sess2.read("w"), want["w"])
+        sess2.restore(path)
+        assert sess2.global_step() == step == 3
+        for k in ("w", "b"):
+            assert np.array_equal(sess2.read(k).view(np.uint32), want[k].view(np.uint32))
+            assert np.array_equal(sess2.params[k].cpu().numpy().view(np.uint32),
+                                  want[k].view(np.uint32))
+        sess2.close()
+    finally:
+        for s in servers2:
+            s.endpoint.stop_event.set()

@@ -35,7 +35,7 @@ def replica_cmd(extra):
             "--job_name", "{job_name}", "--worker_index", "{task_index}"] + extra
 
 
-def oracle_mnist_replica(n_workers, rounds, mode):
+def oracle_mnist_replica(n_workers, rounds, mode, aggregate=None):
     """The same run on the CPU: variables placed on 1 ps task, seeded batches
     rng(1234 + worker), numpy gradients, oracle Adam(0.01)."""
     from tfmesos_b200 import engine
@@ -62,7 +62,7 @@ def oracle_mnist_replica(n_workers, rounds, mode):
             for k, g in zip(NAMES, gs):
                 _, off, _, numel = lay.entries[k]
                 slots[w, off:off + numel] = g.ravel()
-        shard.round(slots, mode)
+        shard.round(slots if aggregate is None else slots[:aggregate], mode)
     out = {}
     for k in NAMES:
         _, off, shape, numel = lay.entries[k]
@@ -94,6 +94,22 @@ def test_mnist_replica_sync_replicas_two_workers_matches_oracle(tmp_path):
     got = np.load(dump)
     want, step = oracle_mnist_replica(2, 8, o.SYNC_MEAN)
     assert int(got["global_step"]) == step == 8
+    for k in NAMES:
+        np.testing.assert_allclose(got[k], want[k], rtol=2e-3, atol=2e-4, err_msg=k)
+
+
+def test_mnist_replica_sync_replicas_to_aggregate_two_of_three(tmp_path):
+    """replicas_to_aggregate < num_workers (mnist_replica.py:64-67,109-113): each
+    round averages 2 of the 3 gradients (workers 0 and 1 in the serialisable
+    schedule), worker 2's is dropped as stale; still one global step per round."""
+    dump = str(tmp_path / "final.npz")
+    out = tfrun(["-w", "3", "-s", "1"] + replica_cmd(
+        ["--train_steps", "6", "--sync_replicas", "--replicas_to_aggregate", "2",
+         "--dump", dump]))
+    assert "global step: 6" in out
+    got = np.load(dump)
+    want, step = oracle_mnist_replica(3, 6, o.SYNC_MEAN, aggregate=2)
+    assert int(got["global_step"]) == step == 6
     for k in NAMES:
         np.testing.assert_allclose(got[k], want[k], rtol=2e-3, atol=2e-4, err_msg=k)
 

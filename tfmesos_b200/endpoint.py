@@ -125,6 +125,30 @@ class Endpoint(object):
     def do_set_hyper(self, key, hyper):
         self.shards[key][0].set_hyper(*hyper)
 
+    # checkpoints of this task's shards (tf.train.Supervisor(logdir=...) stand-in,
+    # examples/mnist/mnist_replica.py:165-170); one file per PS task
+    class _Hosted(object):
+        def __init__(self, shard):
+            self.shard = shard
+            self.spec = type('Spec', (), {'nelem': shard.nelem, 'off': 0})()
+
+    def _as_cluster(self):
+        view = type('View', (), {})()
+        view.servers = {key: self._Hosted(entry[0]) for key, entry in self.shards.items()}
+        return view
+
+    def do_save(self, path):
+        from . import checkpoint
+        self.stream().synchronize()
+        return checkpoint.save(self._as_cluster(), path, self.task_index,
+                               len(self.cluster_def.get('ps', [])) or 1)
+
+    def do_restore(self, path):
+        from . import checkpoint
+        self.stream().synchronize()
+        return checkpoint.restore(self._as_cluster(), path, self.task_index,
+                                  len(self.cluster_def.get('ps', [])) or 1)
+
     def do_put(self, name, value):
         with self.lock:
             self.values[name] = value

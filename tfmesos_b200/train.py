@@ -181,10 +181,16 @@ class ParameterClient(object):
                                                self.applied[spec.key], self.stream)
         self.stream.synchronize()
 
-    def minimize(self, mode=psx.MODE_ASYNC_ORDERED):
+    def minimize(self, mode=psx.MODE_ASYNC_ORDERED, replicas_to_aggregate=None):
         """PUSH this worker's gradients and have every PS apply them (async: this
         worker's slot alone, one global step), then PULL the result -- one
-        ``sess.run([train_step, global_step])`` (mnist_replica.py:204)."""
+        ``sess.run([train_step, global_step])`` (mnist_replica.py:204).
+
+        Aggregated modes take ``replicas_to_aggregate`` (SyncReplicasOptimizer,
+        mnist_replica.py:109-113,148-154): the round's single apply averages that
+        many gradients and the rest are dropped as stale.  Which ones is decided by
+        arrival order in TensorFlow; here, as in the oracle's serialisable
+        schedule, by worker index (slots 0 .. replicas_to_aggregate-1)."""
         import torch
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         self.push_seq += 1
@@ -200,8 +206,10 @@ class ParameterClient(object):
                 # round (SyncReplicasOptimizer's chief queue runner,
                 # mnist_replica.py:159-162,186-190); everyone waits for round n
                 if self.is_chief:
+                    count = self.n_workers if replicas_to_aggregate is None \
+                        else max(1, min(int(replicas_to_aggregate), self.n_workers))
                     endpoint.call(self.ps_addrs[spec.task], 'apply', key=spec.key, mode=mode,
-                                  first_slot=0, count=self.n_workers, wait_seq=self.push_seq)
+                                  first_slot=0, count=count, wait_seq=self.push_seq)
                 self.applied[spec.key] = self.push_seq
         self.pull()
         return self.global_step()
@@ -209,6 +217,16 @@ class ParameterClient(object):
     def global_step(self):
         st = endpoint.call(self.ps_addrs[0], 'state', key=(0, 0))
         return st['global_step']
+
+    def save(self, path):
+        """Checkpoint every PS task's shards (what the chief's Supervisor does
+        with its logdir, mnist_replica.py:165-170); returns the files written."""
+        return [endpoint.call(a, 'save', path=path) for a in self.ps_addrs]
+
+    def restore(self, path):
+        files = [endpoint.call(a, 'restore', path=path) for a in self.ps_addrs]
+        self.pull()
+        return files
 
     def close(self):
         self.worker.close()
