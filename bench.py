@@ -40,6 +40,9 @@ WORKLOADS = {
     "resnet50_bucket": ([("flat", (25_557_032,))], 1, None),
     "mnist_mlp": ([("global_step", ()), ("hid_w", (784, 100)), ("hid_b", (100,)),
                    ("sm_w", (100, 10)), ("sm_b", (10,))], 1, None),
+    "mnist_softmax": ([("W", (784, 10)), ("b", (10,)), ("global_step", ())], 1, None),
+    # the other reading of BASELINE config #3: the PARAMETER is 1e6 x 1e3 (4 GB f32)
+    "embedding_1e6x1e3": ([("P", (1_000_000, 1_000))], 1, None),
 }
 MODES = {"sum": 1, "async": 0, "mean": 2}
 
@@ -233,16 +236,22 @@ def workload_config(args, world, n_full):
 
 
 # ---------------------------------------------------------------- GPU arm ----
-def mnist_section(torch, engine, psx, world, rank, dist, steps=100, warmup=10):
-    """examples/mnist/mnist_replica.py:124-157 -- synthetic [100,784] batches,
-    fwd/bwd by torch on the worker GPU, async-ordered Adam on the PS (one global
-    step per worker push).  Returns global steps/sec."""
-    variables, ps_tasks, placement = WORKLOADS["mnist_mlp"]
-    cl = engine.TorchrunCluster(variables, ps_tasks, engine.AdamOptimizer(0.01),
-                                placement=placement, stripes=1)
-    names = ["hid_w", "hid_b", "sm_w", "sm_b"]
+def mnist_section(torch, engine, psx, world, rank, dist, model="mlp", steps=100, warmup=10):
+    """Full training steps on the reference's two MNIST models, synthetic
+    [100,784] batches, forward/backward by torch on the worker GPU, one PS round
+    per step with async-ordered applies (one global step per worker push):
+      mlp      examples/mnist/mnist_replica.py:124-157  784-100-10, Adam(0.01)
+      softmax  examples/mnist/mnist.py:44-55            784-10, SGD(0.005)
+    Returns global steps/sec."""
+    if model == "mlp":
+        variables, ps_tasks, placement = WORKLOADS["mnist_mlp"]
+        optimizer, names = engine.AdamOptimizer(0.01), ["hid_w", "hid_b", "sm_w", "sm_b"]
+    else:
+        variables, ps_tasks, placement = WORKLOADS["mnist_softmax"]
+        optimizer, names = engine.GradientDescentOptimizer(0.005), ["W", "b"]
+    cl = engine.TorchrunCluster(variables, ps_tasks, optimizer, placement=placement, stripes=1)
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    if rank == 0:
+    if rank == 0 and model == "mlp":
         import numpy as np
         rng = np.random.default_rng(1)
         cl.set_variable("hid_w", np.clip(rng.standard_normal((784, 100)), -2, 2) / 28)
@@ -257,9 +266,13 @@ def mnist_section(torch, engine, psx, world, rank, dist, steps=100, warmup=10):
     def fwd_bwd():
         x.uniform_(0.0, 1.0)                    # a fresh synthetic batch every step
         ps = [wk.params[k].detach().requires_grad_(True) for k in names]
-        h = torch.relu(x @ ps[0] + ps[1])
-        p = torch.softmax(h @ ps[2] + ps[3], 1)
-        loss = -(y * torch.log(torch.clamp(p, 1e-10, 1.0))).sum()
+        if model == "mlp":
+            h = torch.relu(x @ ps[0] + ps[1])
+            p = torch.softmax(h @ ps[2] + ps[3], 1)
+            loss = -(y * torch.log(torch.clamp(p, 1e-10, 1.0))).sum()
+        else:
+            p = torch.softmax(x @ ps[0] + ps[1], 1)
+            loss = -(y * torch.log(p)).sum()
         grads = torch.autograd.grad(loss, ps)
         for k, gr in zip(names, grads):
             wk.grads[k].copy_(gr)
@@ -303,10 +316,13 @@ def mnist_section(torch, engine, psx, world, rank, dist, steps=100, warmup=10):
     t = torch.tensor([dt], dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    n_par = n_params("mnist_mlp" if model == "mlp" else "mnist_softmax")
     out = {"global_steps_per_sec": steps * world / t.item(), "rounds": steps,
-           "workers": world, "params": n_params("mnist_mlp"),
-           "model": "784-100-10 MLP, batch 100, Adam 0.01, async-ordered",
+           "workers": world, "params": n_par,
+           "model": ("784-100-10 MLP, batch 100, Adam 0.01, async-ordered" if model == "mlp"
+                     else "784-10 softmax regression, batch 100, SGD 0.005, async-ordered"),
            "worker_compute": "CUDA graph" if graph is not None else "eager",
+           "push_pull_GBps": steps * world * n_par * 8 / t.item() / 1e9,
            "timing": "CUDA events on the worker stream over %d rounds, max over ranks" % steps}
     cl.close()
     return out
@@ -486,9 +502,10 @@ def run_b200(args):
     # clocks were sampled across all timed regions above (headline, staged, e2e)
     clocks = sampler.stop() if rank == 0 else None
 
-    mnist = None
+    mnist = softmax = None
     if not args.no_mnist:
-        mnist = mnist_section(torch, engine, psx, world, rank, dist)
+        mnist = mnist_section(torch, engine, psx, world, rank, dist, "mlp")
+        softmax = mnist_section(torch, engine, psx, world, rank, dist, "softmax")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -512,6 +529,7 @@ def run_b200(args):
             "e2e": e2e,
             "cpu_baseline": cpu,
             "mnist_replica": mnist,
+            "mnist_softmax_sgd": softmax,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
