@@ -169,3 +169,11 @@ def test_tfrun_cli_runs_and_expands_arguments():
     text = out.stdout.decode()
     assert "[worker:0] probe child worker_0.json" in text
     assert "[worker:1] probe child worker_1.json" in text
+
+
+def test_unplaceable_job_fails_loudly_instead_of_waiting_for_more_offers():
+    """One box = one offer: asking for more GPUs than it has must raise, not hang
+    (on Mesos the reference would keep waiting for further offers)."""
+    with pytest.raises(RuntimeError, match="cannot place"):
+        with tfmesos_b200.cluster([dict(name="worker", num=2, gpus=4096)], quiet=True):
+            pass

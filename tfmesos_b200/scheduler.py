@@ -384,6 +384,7 @@ class LocalSchedulerDriver(object):
         self.sched = sched
         self.framework = framework
         self.children = {}                 # task id -> Popen
+        self.held = {}                     # task id -> resources taken from the offer
         self.lock = threading.Lock()
         self.stopping = False
         self.suppressed = False
@@ -420,6 +421,20 @@ class LocalSchedulerDriver(object):
         self.reaper.daemon = True
         self.reaper.start()
         self._call(self.sched.resourceOffers, self, [self._offer()])
+        self._check_placeable()
+
+    def _check_placeable(self):
+        """A Mesos cluster may offer more later; this box never will.  Tasks that
+        did not fit the one local offer would leave start() waiting for ever, so
+        fail loudly instead (deviation from the reference, which keeps waiting)."""
+        tasks = getattr(self.sched, 'tasks', {})
+        left = ['%s:%s' % (t.job_name, t.task_index) for t in tasks.values() if not t.offered]
+        if left and self.sched.callback_error is None:
+            self.sched.callback_error = RuntimeError(
+                'this box cannot place %s: it offers %.0f cpus, %.0f MB, gpus %s -- '
+                'lower -Cw/-Cs/-Mw/-Ms/-Gw/-Gs or the task counts'
+                % (', '.join(left), float(os.cpu_count() or 1), host_memory_mb(),
+                   visible_gpus() or 'none'))
 
     # -- what the scheduler asks of the driver -----------------------------
     def launchTasks(self, offer_id, infos):
@@ -427,14 +442,18 @@ class LocalSchedulerDriver(object):
             env = dict(os.environ)
             for var in ti.command.environment.variables:
                 env[var.name] = var.value
+            held = {'cpus': 0.0, 'mem': 0.0, 'gpus': []}
             for res in ti.resources:
                 if res.name == 'cpus':
-                    self.free['cpus'] -= res.scalar.value
+                    held['cpus'] = res.scalar.value
                 elif res.name == 'mem':
-                    self.free['mem'] -= res.scalar.value
+                    held['mem'] = res.scalar.value
                 elif res.name == 'gpus':
-                    used = res.set.item if res.type == 'SET' else []
-                    self.free['gpus'] = [g for g in self.free['gpus'] if g not in used]
+                    held['gpus'] = list(res.set.item) if res.type == 'SET' else []
+            self.free['cpus'] -= held['cpus']
+            self.free['mem'] -= held['mem']
+            self.free['gpus'] = [g for g in self.free['gpus'] if g not in held['gpus']]
+            self.held[ti.task_id.value] = held
             proc = subprocess.Popen(ti.command.value, shell=True, env=env,
                                     start_new_session=True)
             with self.lock:
@@ -449,6 +468,7 @@ class LocalSchedulerDriver(object):
     def reviveOffers(self):
         self.suppressed = False
         self._call(self.sched.resourceOffers, self, [self._offer()])
+        self._check_placeable()
 
     def _reap(self):
         while not self.stopping:
@@ -459,6 +479,11 @@ class LocalSchedulerDriver(object):
                     if rc is not None:
                         done.append((task_id, rc))
                         del self.children[task_id]
+                        held = self.held.pop(task_id, None)
+                        if held:           # a finished task gives its slice back
+                            self.free['cpus'] += held['cpus']
+                            self.free['mem'] += held['mem']
+                            self.free['gpus'] = self.free['gpus'] + held['gpus']
             for task_id, rc in done:
                 update = AttrDict(state='TASK_FINISHED' if rc == 0 else 'TASK_FAILED',
                                   message='exit status %s' % rc)
