@@ -24,18 +24,44 @@ from .utils import recv, send
 logger = logging.getLogger(__name__)
 
 
+_channels = threading.local()
+
+
+def _channel(addr):
+    """One kept-alive connection per (thread, endpoint): a training step makes a
+    request or two per PS task, and a TCP connect per request would dominate."""
+    pool = getattr(_channels, 'pool', None)
+    if pool is None:
+        pool = _channels.pool = {}
+    conn = pool.get(addr)
+    if conn is None:
+        host, port = addr.rsplit(':', 1)
+        conn = socket.create_connection((host, int(port)), timeout=120)
+        conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+        pool[addr] = conn
+    return conn
+
+
 def call(addr, method, **kw):
     """One request to the endpoint at 'host:port' (accepts 'grpc://host:port',
     the form in ``cluster.targets``, scheduler.py:284)."""
     if addr.startswith('grpc://'):
         addr = addr[len('grpc://'):]
-    host, port = addr.rsplit(':', 1)
-    conn = socket.create_connection((host, int(port)), timeout=120)
-    try:
-        send(conn, (method, kw))
-        status, payload = recv(conn)
-    finally:
-        conn.close()
+    for attempt in (0, 1):
+        conn = _channel(addr)
+        try:
+            send(conn, (method, kw))
+            status, payload = recv(conn)
+            break
+        except (OSError, AssertionError, EOFError):
+            # stale kept-alive connection (endpoint restarted): reconnect once
+            _channels.pool.pop(addr, None)
+            try:
+                conn.close()
+            except OSError:
+                pass
+            if attempt:
+                raise
     if status != 'ok':
         raise RuntimeError('endpoint %s: %s failed: %s' % (addr, method, payload))
     return payload
@@ -48,7 +74,7 @@ class Endpoint(object):
         self.cluster_def = cluster_def
         self.gpus = gpus
         self.lock = threading.RLock()
-        self.shards = {}          # key -> (psx.Shard, applies enqueued)
+        self.shards = {}          # key -> [psx.Shard, applies enqueued, global steps enqueued]
         self.values = {}          # tiny value store for plumbing graphs (plus.py)
         self.stop_event = threading.Event()
         self._device = None
@@ -87,7 +113,7 @@ class Endpoint(object):
             if key not in self.shards:
                 lr, b1, b2, eps = hyper
                 shard = psx.Shard(self.device(), nelem, opt, lr, b1, b2, eps, n_slots, wire)
-                self.shards[key] = [shard, 0]
+                self.shards[key] = [shard, 0, 0]
             return self.shards[key][0].export()
 
     def do_shard_handle(self, key):
@@ -102,13 +128,17 @@ class Endpoint(object):
 
     def do_apply(self, key, mode, first_slot, count, wait_seq, fused=False):
         """Enqueue wait(flags) + the fused reduce/apply kernel on this task's
-        stream; returns the apply_seq the caller's pull must wait for."""
+        stream; returns the apply_seq the caller's pull must wait for and the
+        global_step that apply produces (every apply of a shard goes through this
+        method, so the host-side count is exact and needs no device sync)."""
+        from . import psx
         with self.lock:
             entry = self.shards[key]
             fn = entry[0].round if fused else entry[0].apply
             fn(mode, first_slot, count, wait_seq, self.stream())
             entry[1] += 1
-            return entry[1]
+            entry[2] += count if mode == psx.MODE_ASYNC_ORDERED else 1
+            return {'applied': entry[1], 'global_step': entry[2]}
 
     def do_set_values(self, key, which, off, data):
         import numpy as np
@@ -146,8 +176,13 @@ class Endpoint(object):
     def do_restore(self, path):
         from . import checkpoint
         self.stream().synchronize()
-        return checkpoint.restore(self._as_cluster(), path, self.task_index,
-                                  len(self.cluster_def.get('ps', [])) or 1)
+        fn = checkpoint.restore(self._as_cluster(), path, self.task_index,
+                                len(self.cluster_def.get('ps', [])) or 1)
+        with self.lock:
+            for entry in self.shards.values():
+                st = entry[0].state()
+                entry[2] = st['global_step']
+        return fn
 
     def do_put(self, name, value):
         with self.lock:
@@ -180,13 +215,19 @@ class Endpoint(object):
 
     # ---- server loop ------------------------------------------------------------
     def handle(self, conn):
+        """Serve requests on one (kept-alive) connection until the peer closes."""
         try:
-            method, kw = recv(conn)
-            try:
-                result = getattr(self, 'do_' + method)(**kw)
-                send(conn, ('ok', result))
-            except Exception:
-                send(conn, ('err', traceback.format_exc()))
+            conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+            while not self.stop_event.is_set():
+                try:
+                    method, kw = recv(conn)
+                except (AssertionError, OSError, EOFError):
+                    break                      # peer closed
+                try:
+                    result = getattr(self, 'do_' + method)(**kw)
+                    send(conn, ('ok', result))
+                except Exception:
+                    send(conn, ('err', traceback.format_exc()))
         except Exception:
             logger.exception('bad request')
         finally:

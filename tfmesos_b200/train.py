@@ -142,6 +142,7 @@ class ParameterClient(object):
         self.params, self.grads = self.worker.params, self.worker.grads
         self.stream = torch.cuda.Stream(device=device)
         self.push_seq = 0
+        self.step_base = 0            # global_step at session start (after a restore)
         self.applied = {spec.key: 0 for spec in self.topo.shards}
         if self.is_chief:
             for name, value in (init or {}).items():
@@ -195,12 +196,15 @@ class ParameterClient(object):
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         self.push_seq += 1
         self.worker.push(self.push_seq, self.stream)
+        step = None
         for spec in self.topo.shards:
             if mode == psx.MODE_ASYNC_ORDERED:
                 # this worker's gradient alone: one ApplyAdam, one global step
-                self.applied[spec.key] = endpoint.call(
-                    self.ps_addrs[spec.task], 'apply', key=spec.key, mode=mode,
-                    first_slot=self.index, count=1, wait_seq=self.push_seq)
+                r = endpoint.call(self.ps_addrs[spec.task], 'apply', key=spec.key, mode=mode,
+                                  first_slot=self.index, count=1, wait_seq=self.push_seq)
+                self.applied[spec.key] = r['applied']
+                if spec.key == (0, 0):
+                    step = r['global_step']
             else:
                 # aggregated modes: the chief triggers the single apply of the
                 # round (SyncReplicasOptimizer's chief queue runner,
@@ -211,8 +215,9 @@ class ParameterClient(object):
                     endpoint.call(self.ps_addrs[spec.task], 'apply', key=spec.key, mode=mode,
                                   first_slot=0, count=count, wait_seq=self.push_seq)
                 self.applied[spec.key] = self.push_seq
+                step = self.step_base + self.push_seq       # one global step per round
         self.pull()
-        return self.global_step()
+        return step
 
     def global_step(self):
         st = endpoint.call(self.ps_addrs[0], 'state', key=(0, 0))
@@ -225,6 +230,7 @@ class ParameterClient(object):
 
     def restore(self, path):
         files = [endpoint.call(a, 'restore', path=path) for a in self.ps_addrs]
+        self.step_base = self.global_step() - self.push_seq
         self.pull()
         return files
 
