@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define PSX_ABI_VERSION 6
+#define PSX_ABI_VERSION 7
 
 /* error codes */
 #define PSX_OK 0
@@ -126,6 +126,16 @@ int psx_set_state(uint64_t id, float b1p, float b2p, int64_t step);
  * and SyncReplicasOptimizer's aggregation (mnist_replica.py:148-154). */
 int psx_apply(uint64_t id, int mode, int first_slot, int count, uint32_t wait_seq,
               void *stream);
+
+/* The same over elements [elem_off, elem_off + elem_n) of the shard only (elem_off
+ * a multiple of 4; elem_n = 0 means the whole shard).  finish = 0 keeps the round
+ * open: the beta powers, global_step and apply_seq move only with the launch that
+ * passes finish = 1.  For row-block data parallelism (each worker owns a block of
+ * rows of an embedding-like variable and pushes / pulls only that block): one
+ * psx_apply_range per block with that block's owner as the only slot.
+ * Replaces: the sparse (IndexedSlices) flavour of the apply ops for dense blocks. */
+int psx_apply_range(uint64_t id, int mode, int first_slot, int count, uint64_t elem_off,
+                    uint64_t elem_n, int finish, uint32_t wait_seq, void *stream);
 
 /* Only the waiting half of psx_apply / psx_round: make `stream` wait until slots
  * [first_slot, first_slot+count) carry seq >= wait_seq.  Lets a caller bracket

@@ -584,3 +584,50 @@ def test_shard_larger_than_2_pow_31_elements():
     finally:
         c.close()
         shard.destroy()
+
+
+@pytest.mark.parametrize("opt", [psx.OPT_SGD, psx.OPT_ADAM])
+def test_row_block_data_parallel_partial_applies(opt):
+    """Row-block data parallelism over an embedding-like variable (the scaled NMF's
+    W: each worker holds a block of rows of R, so its dW is non-zero only in its own
+    rows): every worker pushes and pulls ONLY its block, the PS runs one
+    psx_apply_range per block with that block's owner as the single slot, and only
+    the last launch closes the round.  Equals ONE oracle apply of the assembled
+    gradient, bit for bit; beta powers / global_step advance once."""
+    torch = _torch()
+    rows, rank, W = 1003, 36, 4                      # ragged: 1003 rows over 4 workers
+    n = rows * rank
+    bounds = [(rows * k // W) * rank for k in range(W + 1)]
+    shard = psx.Shard(0, n, opt, lr=0.01, n_slots=W)
+    ref = o.CShard(n, opt, lr=0.01)
+    rng = np.random.default_rng(23)
+    init = rng.standard_normal(n).astype(F)
+    shard.set_values(psx.VAR, init)
+    ref.var[:] = init
+    clients = [psx.Client(shard.export(), 0, w) for w in range(W)]
+    for w, c in enumerate(clients):
+        shard.register_client(w, c.export())
+    try:
+        for r in range(1, 4):
+            full = (rng.standard_normal(n) * 0.1).astype(F)
+            dev = torch.from_numpy(full).cuda()
+            for w in range(W):
+                lo, hi = bounds[w], bounds[w + 1]
+                clients[w].push(dev.data_ptr() + lo * 4, hi - lo, off=lo, seq=r)
+            for w in range(W):
+                lo, hi = bounds[w], bounds[w + 1]
+                shard.apply_range(psx.MODE_SUM, w, 1, lo, hi - lo, finish=(w == W - 1),
+                                  wait_seq=r)
+            ref.round(full[None, :], o.SUM)
+        out = torch.zeros(n, device="cuda")
+        for w in range(W):
+            lo, hi = bounds[w], bounds[w + 1]
+            clients[w].pull(out.data_ptr() + lo * 4, hi - lo, off=lo, wait_seq=3)
+        torch.cuda.synchronize()
+        check_against(shard, ref, n, opt)
+        assert_bits_equal(out.cpu().numpy(), ref.var, "pulled blocks")
+        assert shard.state()["apply_seq"] == 3 and shard.state()["global_step"] == 3
+    finally:
+        for c in clients:
+            c.close()
+        shard.destroy()

@@ -319,19 +319,30 @@ int launch_copy(void *dst, int dst_t, const void *src, int src_t, uint64_t n, in
     return PSX_OK;
 }
 
+// A launch covers elements [range.off, range.off + range.n) of the shard (multiples
+// of 4); finish = 0 keeps the round open (no beta-power / step / apply_seq update).
+struct ApplyRange {
+    size_t off, n;
+    int finish;
+};
+
 template <int OPT, int MODE, bool SCATTER, typename SRC>
-void launch_apply_t(Shard *s, SRC src, int count, const PeerSet &peers, cudaStream_t st)
+void launch_apply_t(Shard *s, SRC src, int count, const PeerSet &peers, cudaStream_t st,
+                    const ApplyRange &r)
 {
-    const size_t n4 = s->lay.nelem_pad / 4;
-    const int grid = grid_for(n4, kApplyThreads, s->sm_count, 3);
+    const size_t n4 = r.n / 4;
+    const int grid = grid_for(n4 ? n4 : 1, kApplyThreads, s->sm_count, 3);
     k_apply<OPT, MODE, SCATTER, SRC><<<grid, kApplyThreads, 0, st>>>(
-        s->hdr(), (float4 *)s->var(), (float4 *)s->m(), (float4 *)s->v(), src, count, n4, peers);
+        s->hdr(), (float4 *)(s->var() + r.off), (float4 *)(s->m() + r.off),
+        (float4 *)(s->v() + r.off), src, count, n4, peers, r.finish);
 }
 
 template <bool SCATTER, typename SRC>
-int launch_apply(Shard *s, int mode, SRC src, int count, const PeerSet &peers, cudaStream_t st)
+int launch_apply(Shard *s, int mode, SRC src, int count, const PeerSet &peers, cudaStream_t st,
+                 ApplyRange r = ApplyRange{0, 0, 1})
 {
-#define PSX_AP(O, M) launch_apply_t<O, M, SCATTER, SRC>(s, src, count, peers, st)
+    if (r.n == 0 && r.off == 0) r.n = s->lay.nelem_pad;
+#define PSX_AP(O, M) launch_apply_t<O, M, SCATTER, SRC>(s, src, count, peers, st, r)
     const int opt = s->lay.opt;
     if (opt == PSX_OPT_SGD && mode == PSX_MODE_ASYNC_ORDERED) PSX_AP(PSX_OPT_SGD, PSX_MODE_ASYNC_ORDERED);
     else if (opt == PSX_OPT_SGD && mode == PSX_MODE_SUM) PSX_AP(PSX_OPT_SGD, PSX_MODE_SUM);
@@ -631,24 +642,43 @@ int psx_shard_ptr(uint64_t id, int which, void **out_dev_ptr)
     return PSX_OK;
 }
 
-int psx_apply(uint64_t id, int mode, int first_slot, int count, uint32_t wait_seq, void *stream)
+int psx_apply_range(uint64_t id, int mode, int first_slot, int count, uint64_t elem_off,
+                    uint64_t elem_n, int finish, uint32_t wait_seq, void *stream)
 {
     Shard *s = find(g_shards, id);
     if (!s) return fail(PSX_EINVAL, "unknown shard id");
     int rc = check_range(first_slot, count, s->lay.n_slots);
     if (rc) return rc;
+    if (elem_n == 0) {                      // whole shard
+        elem_off = 0;
+        elem_n = s->lay.nelem_pad;
+    } else {
+        if (elem_off % 4) return fail(PSX_EINVAL, "elem_off must be a multiple of 4");
+        if (elem_off + elem_n > s->lay.nelem_pad)
+            return fail(PSX_EINVAL, "apply range [%llu,+%llu) outside the shard", (unsigned long long)elem_off, (unsigned long long)elem_n);
+        if (elem_n % 4 && elem_off + elem_n < s->lay.nelem)
+            return fail(PSX_EINVAL, "an inner apply range must be a multiple of 4 elements");
+        elem_n = (elem_n + 3) / 4 * 4;      // the padding up to nelem_pad is always allocated
+        if (elem_off + elem_n > s->lay.nelem_pad) elem_n = s->lay.nelem_pad - elem_off;
+    }
     PSX_DEVICE(s->device);
     rc = wait_slots(s, first_slot, count, wait_seq, stream);
     if (rc) return rc;
     PeerSet peers;
     memset(&peers, 0, sizeof(peers));
     fill_mirrors(s, &peers);
+    const ApplyRange r{(size_t)elem_off, (size_t)elem_n, finish ? 1 : 0};
     if (s->lay.wire == PSX_F32) {
-        SlotSrc<float> src{(const float *)s->slot(0), (size_t)s->lay.nelem_pad, first_slot};
-        return launch_apply<false>(s, mode, src, count, peers, (cudaStream_t)stream);
+        SlotSrc<float> src{(const float *)s->slot(0) + elem_off, (size_t)s->lay.nelem_pad, first_slot};
+        return launch_apply<false>(s, mode, src, count, peers, (cudaStream_t)stream, r);
     }
-    SlotSrc<__nv_bfloat16> src{(const __nv_bfloat16 *)s->slot(0), (size_t)s->lay.nelem_pad, first_slot};
-    return launch_apply<false>(s, mode, src, count, peers, (cudaStream_t)stream);
+    SlotSrc<__nv_bfloat16> src{(const __nv_bfloat16 *)s->slot(0) + elem_off, (size_t)s->lay.nelem_pad, first_slot};
+    return launch_apply<false>(s, mode, src, count, peers, (cudaStream_t)stream, r);
+}
+
+int psx_apply(uint64_t id, int mode, int first_slot, int count, uint32_t wait_seq, void *stream)
+{
+    return psx_apply_range(id, mode, first_slot, count, 0, 0, 1, wait_seq, stream);
 }
 
 int psx_wait_slots(uint64_t id, int first_slot, int count, uint32_t wait_seq, void *stream)

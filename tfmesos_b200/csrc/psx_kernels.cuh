@@ -475,7 +475,7 @@ template <typename W> struct WireOf<PeerSrc<W>> { using type = W; };
 template <int OPT, int MODE, bool SCATTER, typename SRC>
 __global__ void __launch_bounds__(kApplyThreads, 3)
 k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restrict__ mom,
-        float4 *__restrict__ vel, SRC src, int count, size_t n4, PeerSet peers)
+        float4 *__restrict__ vel, SRC src, int count, size_t n4, PeerSet peers, int finish)
 {
     __shared__ float s_alpha[PSX_MAX_SLOTS];
     const float lr = h->lr, b1 = h->b1, b2 = h->b2, eps = h->eps;
@@ -566,7 +566,12 @@ k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restric
         }
     }
 
-    if (last_cta(&h->ticket) && threadIdx.x == 0) {
+    // finish == 0: a partial (element-range) apply that is not the last of its
+    // round -- it must not advance the beta powers / global_step / apply_seq
+    const bool last = last_cta(&h->ticket);
+    if (last && threadIdx.x == 0 && !finish) {
+        h->ticket = 0;
+    } else if (last && threadIdx.x == 0) {
         const int applies = (MODE == PSX_MODE_ASYNC_ORDERED) ? count : 1;
         if (OPT == PSX_OPT_ADAM) {
             float p1 = h->b1p, p2 = h->b2p;

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libpsx.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 OPT_SGD, OPT_ADAM = 0, 1
 MODE_ASYNC_ORDERED, MODE_SUM, MODE_SYNC_MEAN = 0, 1, 2
 F32, BF16 = 0, 1
@@ -54,6 +54,7 @@ SIGNATURES = {
                              ctypes.POINTER(_u32)]),
     "psx_set_state": (_i32, [_u64, ctypes.c_float, ctypes.c_float, ctypes.c_int64]),
     "psx_apply": (_i32, [_u64, _i32, _i32, _i32, _u32, _vp]),
+    "psx_apply_range": (_i32, [_u64, _i32, _i32, _i32, _u64, _u64, _i32, _u32, _vp]),
     "psx_wait_slots": (_i32, [_u64, _i32, _i32, _u32, _vp]),
     "psx_shard_open": (_i32, [_vp, _i32, _i32, ctypes.POINTER(_u64)]),
     "psx_shard_close": (_i32, [_u64]),
@@ -218,6 +219,12 @@ class Shard(object):
     def apply(self, mode, first_slot=0, count=1, wait_seq=0, stream=None):
         _check(lib().psx_apply(self.id, int(mode), int(first_slot), int(count),
                                int(wait_seq), _stream_ptr(stream)))
+
+    def apply_range(self, mode, first_slot, count, elem_off, elem_n, finish=True, wait_seq=0,
+                    stream=None):
+        _check(lib().psx_apply_range(self.id, int(mode), int(first_slot), int(count),
+                                     int(elem_off), int(elem_n), int(bool(finish)),
+                                     int(wait_seq), _stream_ptr(stream)))
 
     def wait_slots(self, first_slot, count, wait_seq, stream=None):
         _check(lib().psx_wait_slots(self.id, int(first_slot), int(count), int(wait_seq),
