@@ -445,6 +445,12 @@ __device__ __forceinline__ float4 div4(const float4 &a, float d)
 
 constexpr int kApplyThreads = 256;
 constexpr int kSlotChunk = 4;  // gradient vectors in flight per thread
+#ifndef PSX_APPLY_MIN_CTAS
+#define PSX_APPLY_MIN_CTAS 3   // resident CTAs per SM the register budget is cut for
+#endif
+#ifndef PSX_PREFETCH_STATE
+#define PSX_PREFETCH_STATE 0   // 1: also request var/m/v of the next iteration early
+#endif
 
 // Where slot s's gradient vector i comes from.
 template <typename WIRE> struct SlotSrc {            // landing slots in the shard
@@ -473,7 +479,7 @@ template <typename W> struct WireOf<PeerSrc<W>> { using type = W; };
 // Fused reduce + apply over a whole shard (n4 vectors).  SCATTER: also write
 // the new parameters into every bound worker parameter buffer (psx_round).
 template <int OPT, int MODE, bool SCATTER, typename SRC>
-__global__ void __launch_bounds__(kApplyThreads, 3)
+__global__ void __launch_bounds__(kApplyThreads, PSX_APPLY_MIN_CTAS)
 k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restrict__ mom,
         float4 *__restrict__ vel, SRC src, int count, size_t n4, PeerSet peers, int finish)
 {
@@ -509,13 +515,34 @@ k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restric
         for (int k = 0; k < kSlotChunk; ++k)
             if (k < count) gn[k] = src.load(k, i);
     }
+#if PSX_PREFETCH_STATE
+    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f), mn = xn, vn = xn;
+    if (i < n4) {
+        xn = ld_stream(var + i);
+        if (OPT == PSX_OPT_ADAM) {
+            mn = ld_stream(mom + i);
+            vn = ld_stream(vel + i);
+        }
+    }
+#endif
     for (; i < n4; i += stride) {
+#if PSX_PREFETCH_STATE
+        float4 x = xn, m = mn, v = vn;
+        if (i + stride < n4) {
+            xn = ld_stream(var + i + stride);
+            if (OPT == PSX_OPT_ADAM) {
+                mn = ld_stream(mom + i + stride);
+                vn = ld_stream(vel + i + stride);
+            }
+        }
+#else
         float4 x = ld_stream(var + i);
         float4 m = make_float4(0.f, 0.f, 0.f, 0.f), v = m;
         if (OPT == PSX_OPT_ADAM) {
             m = ld_stream(mom + i);
             v = ld_stream(vel + i);
         }
+#endif
         float4 g[kSlotChunk];
         if (PF) {
 #pragma unroll

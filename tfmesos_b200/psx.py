@@ -10,7 +10,8 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpsx.so")
+# TFMESOS_PSX_LIB selects another build of the same ABI (kernel A/B experiments)
+LIB_PATH = os.environ.get("TFMESOS_PSX_LIB") or os.path.join(HERE, "lib", "libpsx.so")
 
 ABI_VERSION = 7
 OPT_SGD, OPT_ADAM = 0, 1
