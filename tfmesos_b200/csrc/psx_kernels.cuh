@@ -100,12 +100,10 @@ __device__ __forceinline__ void st_stream(uint2 *p, const uint2 &v)
 // 4-element vectors of the two wire types
 template <typename T> struct Vec4;
 template <> struct Vec4<float> {
-    using type = float4;
     static __device__ __forceinline__ float4 load(const float *p) { return ld_stream((const float4 *)p); }
     static __device__ __forceinline__ void store(float *p, const float4 &v) { st_stream((float4 *)p, v); }
 };
 template <> struct Vec4<__nv_bfloat16> {
-    using type = uint2;
     static __device__ __forceinline__ float4 load(const __nv_bfloat16 *p)
     {
         uint2 u = ld_stream((const uint2 *)p);
@@ -412,9 +410,6 @@ __device__ __forceinline__ float adam_alpha(float lr, float b1p, float b2p)
     float s = __fsqrt_rn(__fsub_rn(1.0f, b2p));
     return __fdiv_rn(__fmul_rn(lr, s), __fsub_rn(1.0f, b1p));
 }
-
-#define PSX_FOR4(expr_x, expr_y, expr_z, expr_w) \
-    do { expr_x; expr_y; expr_z; expr_w; } while (0)
 
 template <int OPT>
 __device__ __forceinline__ void apply4(float4 &x, float4 &m, float4 &v, const float4 &g,
