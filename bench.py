@@ -507,11 +507,21 @@ def run_b200(args):
         mnist = mnist_section(torch, engine, psx, world, rank, dist, "mlp")
         softmax = mnist_section(torch, engine, psx, world, rank, dist, "softmax")
 
-    cpu = None
+    cpu = cpu_grpc = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)          # the CPU arm gets every host core
         cb = cpu_ps(args, steps=5, warmup=1)
         cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        try:
+            # the same path over the transport the reference actually selects
+            # (protocol='grpc'): loopback gRPC, one RPC per variable per direction
+            from oracle import cpu_ps_grpc
+            cpu_grpc = cpu_ps_grpc.time_round(min(n_full, 10_000_000), steps=3, warmup=1)
+            cpu_grpc.update({"kind": "port", "transport": "python grpcio, loopback, raw bytes "
+                             "(TensorFlow's C++ gRPC core moves tensors a few times faster; "
+                             "the memcpy figure above is the upper bound for this path)"})
+        except Exception as exc:
+            cpu_grpc = {"unavailable": str(exc)[:200]}
 
     if rank == 0:
         line = {
@@ -528,6 +538,7 @@ def run_b200(args):
             "staged_path": staged,
             "e2e": e2e,
             "cpu_baseline": cpu,
+            "cpu_baseline_grpc": cpu_grpc,
             "mnist_replica": mnist,
             "mnist_softmax_sgd": softmax,
         }
