@@ -170,3 +170,18 @@ def test_in_graph_mnist_runs_and_learns():
     assert r.returncode == 0, r.stderr.decode()[-3000:]
     acc = float(r.stdout.decode().strip().splitlines()[-1])
     assert 0.5 < acc <= 1.0
+
+
+@pytest.mark.multigpu
+def test_mnist_replica_pinned_workers_reach_ps_tasks_on_gpus_they_cannot_see():
+    """`tfrun -Gw 1`: every worker is pinned to ONE GPU through
+    CUDA_VISIBLE_DEVICES, the two ps tasks sit on GPU 0 and GPU 1 -- so worker:0
+    maps a shard that lives on a GPU outside its visible set (and whose ordinal
+    in the ps task's numbering does not exist in the worker's).  CUDA IPC maps it
+    regardless; ordinals from another process must never be interpreted locally."""
+    out = tfrun(["-w", "2", "-s", "2", "-Gw", "1", "--worker-logs", "*"] +
+                replica_cmd(["--train_steps", "24"]))
+    steps = [int(m) for m in re.findall(r"\(global step: (\d+)\)", out)]
+    assert steps and 24 <= max(steps) <= 25
+    val = float(re.search(r"validation cross entropy = ([-+0-9.eE]+|nan|inf)", out).group(1))
+    assert np.isfinite(val)

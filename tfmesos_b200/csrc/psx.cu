@@ -212,10 +212,19 @@ int sm_count_of(int device)
     return n > 0 ? n : 148;
 }
 
+int enable_peer(int device, int peer);
+
+// Maps the object a handle names for use from `device`.  Same process: the raw
+// pointer, after enabling peer access between the two ordinals.  Other process:
+// CUDA IPC, which enables peer access itself (the exporter's ordinal means
+// nothing here -- the importer may see a different set of GPUs through
+// CUDA_VISIBLE_DEVICES, as tfrun -Gw 1 workers do).
 int open_blob(const HandleBlob &b, int device, Mapped *out)
 {
     out->device = b.device;
     if (b.pid == (uint64_t)getpid()) {  // same process: direct pointer
+        int prc = enable_peer(device, b.device);
+        if (prc) return prc;
         std::lock_guard<std::mutex> lk(g_mu);
         char *base = nullptr;
         if (b.kind == KIND_SHARD) {
@@ -703,8 +712,6 @@ int psx_shard_register_client(uint64_t shard_id, int slot, const void *client_ha
         close_mapped(s->client_map[slot]);
         s->mirror[slot] = nullptr;
     }
-    rc = enable_peer(s->device, b.device);
-    if (rc) return rc;
     rc = open_blob(b, s->device, &s->client_map[slot]);
     if (rc) return rc;
     s->mirror[slot] = &((ClientBlock *)s->client_map[slot].base)->applied;
@@ -721,8 +728,6 @@ int psx_shard_open(const void *handle, int device, int slot, uint64_t *out_id)
     if (slot < 0 || slot >= PSX_MAX_SLOTS || (b.n_slots > 0 && slot >= b.n_slots))
         return fail(PSX_EINVAL, "slot %d outside the shard's %d slots", slot,
                     b.n_slots > 0 ? b.n_slots : PSX_MAX_SLOTS);
-    rc = enable_peer(device, b.device);
-    if (rc) return rc;
     Client *c = new Client();
     c->device = device;
     c->slot = slot;
@@ -926,8 +931,6 @@ int psx_shard_register_mailbox(uint64_t shard_id, int slot, const void *mailbox_
         close_mapped(s->mailbox_map[slot]);
         s->mailbox[slot] = nullptr;
     }
-    rc = enable_peer(s->device, b.device);
-    if (rc) return rc;
     rc = open_blob(b, s->device, &s->mailbox_map[slot]);
     if (rc) return rc;
     s->mailbox[slot] = (unsigned int *)s->mailbox_map[slot].base;
@@ -1163,10 +1166,6 @@ int psx_round_bind(uint64_t shard_id, int slot, const void *grad_buf_handle,
         close_mapped(b.param);
         b.valid = false;
     }
-    rc = enable_peer(s->device, g.device);
-    if (rc) return rc;
-    rc = enable_peer(s->device, p.device);
-    if (rc) return rc;
     rc = open_blob(g, s->device, &b.grad);
     if (rc) return rc;
     rc = open_blob(p, s->device, &b.param);
