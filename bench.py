@@ -279,7 +279,13 @@ def mnist_section(torch, engine, psx, world, rank, dist, model="mlp", steps=100,
 
     graph = None
 
+    whole = None
+
     def step():
+        if whole is not None:
+            with torch.cuda.stream(ws):
+                whole.replay()
+            return
         with torch.cuda.stream(ws):
             if graph is not None:
                 graph.replay()
@@ -295,14 +301,27 @@ def mnist_section(torch, engine, psx, world, rank, dist, model="mlp", steps=100,
     # the worker's compute is launch-bound (20-odd tiny kernels): capture it once
     # in a CUDA graph; the PS round stays ordinary launches (its sequence numbers
     # change every step)
+    whole = None
     try:
-        g_ = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_, stream=ws):
-            fwd_bwd()
-        graph = g_
-    except Exception as exc:                    # keep measuring, eagerly
-        sys.stderr.write("mnist: CUDA graph capture failed (%s), running eagerly\n" % exc)
-        graph = None
+        # the whole step -- forward/backward AND the PS round (signal/push, counted
+        # stream waits, apply, pull) -- as ONE graph: a replay is a training step
+        whole = cl.capture_round(psx.MODE_ASYNC_ORDERED, pre=fwd_bwd)
+    except Exception as exc:
+        sys.stderr.write("mnist: whole-step graph capture failed (%s)\n" % str(exc)[:300])
+        whole = None
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+    if whole is None:
+        try:
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_, stream=ws):
+                fwd_bwd()
+            graph = g_
+        except Exception as exc:                # keep measuring, eagerly
+            sys.stderr.write("mnist: CUDA graph capture failed (%s), running eagerly\n" % exc)
+            graph = None
     for _ in range(warmup):
         step()
     cl.barrier()
@@ -321,7 +340,9 @@ def mnist_section(torch, engine, psx, world, rank, dist, model="mlp", steps=100,
            "workers": world, "params": n_par,
            "model": ("784-100-10 MLP, batch 100, Adam 0.01, async-ordered" if model == "mlp"
                      else "784-10 softmax regression, batch 100, SGD 0.005, async-ordered"),
-           "worker_compute": "CUDA graph" if graph is not None else "eager",
+           "worker_compute": ("whole step (fwd/bwd + PS round) in one CUDA graph"
+                              if whole is not None else
+                              "CUDA graph" if graph is not None else "eager"),
            "push_pull_GBps": steps * world * n_par * 8 / t.item() / 1e9,
            "timing": "CUDA events on the worker stream over %d rounds, max over ranks" % steps}
     cl.close()

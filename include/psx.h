@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define PSX_ABI_VERSION 7
+#define PSX_ABI_VERSION 8
 
 /* error codes */
 #define PSX_OK 0
@@ -221,6 +221,25 @@ int psx_mailbox_destroy(uint64_t id);
 int psx_shard_register_mailbox(uint64_t shard_id, int slot, const void *mailbox_handle);
 int psx_wait_mailbox(uint64_t id, uint32_t target, void *stream);
 
+/* Counted (graph-replayable) form of the same rendez-vous: every wait compares
+ * with a CONSTANT and the waiter takes what it waited for off the counter, so a
+ * round is the same command sequence every time and can be replayed from a CUDA
+ * graph (stream memops are graph nodes).
+ *   psx_round_counted / psx_apply_counted: wait for arrivals >= count, launch;
+ *       the kernel's first instruction subtracts `count` from the counter.
+ *   psx_signal_counted: like psx_signal_many, but first takes `consume` (last
+ *       round's n_shards) off the worker's mailbox.
+ *   psx_mailbox_consume: the same subtraction as a 1-thread launch (staged path).
+ * Wait for a round's completion with psx_wait_mailbox(id, n_shards). */
+int psx_round_counted(uint64_t shard_id, int mode, int first_slot, int count, void *stream);
+int psx_apply_counted(uint64_t id, int mode, int first_slot, int count, void *stream);
+int psx_signal_counted(const uint64_t *client_ids, int n, uint32_t seq, uint64_t mailbox_id,
+                       uint32_t consume, void *stream);
+int psx_mailbox_consume(uint64_t id, uint32_t n, void *stream);
+/* Synchronous: set the counter (prime it with n_shards so that the first counted
+ * round consumes the same constant as every later one). */
+int psx_mailbox_set(uint64_t id, uint32_t value);
+
 /* ONE kernel on the PS GPU: gather the bound gradients straight from the
  * workers' HBM (peer loads), reduce in registers in slot order, apply
  * SGD/Adam to var/m/v in place, and scatter the new parameters into every
@@ -246,6 +265,11 @@ int psx_round(uint64_t shard_id, int mode, int first_slot, int count, uint32_t w
 #define PSX_OP_SIGNAL_MANY 8   /* ptr=uint64 client ids, n=count, seq                */
 #define PSX_OP_WAIT_ARRIVALS 9 /* id=shard, waits for arrivals >= seq * c            */
 #define PSX_OP_WAIT_MAILBOX 10 /* id=mailbox, waits for counter >= seq * c           */
+#define PSX_OP_ROUND_COUNTED 11   /* id=shard a=mode b=first_slot c=count            */
+#define PSX_OP_APPLY_COUNTED 12   /* id=shard a=mode b=first_slot c=count            */
+#define PSX_OP_SIGNAL_COUNTED 13  /* ptr=client ids n=count id=mailbox c=consume seq  */
+#define PSX_OP_MAILBOX_WAIT 14    /* id=mailbox, waits for counter >= c               */
+#define PSX_OP_MAILBOX_CONSUME 15 /* id=mailbox, counter -= c                         */
 typedef struct psx_op {
     int32_t op, a, b, c;
     uint64_t id, off, n;

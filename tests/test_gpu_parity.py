@@ -631,3 +631,39 @@ def test_row_block_data_parallel_partial_applies(opt):
         for c in clients:
             c.close()
         shard.destroy()
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_captured_round_replays_bit_exact(fused):
+    """A PS round captured in a CUDA graph (counted rendez-vous: constant stream-wait
+    values, consumed counters) and replayed N times equals N oracle rounds."""
+    torch = _torch()
+    variables = [("w", (500, 64)), ("b", (64,))]
+    cl = engine.TorchrunCluster(variables, 1, engine.AdamOptimizer(0.01), stripes=2,
+                                fused=fused, device=0)
+    n = cl.layout.bucket_nelem[0]
+    ref = o.CShard(n, o.ADAM, lr=0.01)
+    rng = np.random.default_rng(29)
+    try:
+        g = (rng.standard_normal(n) * 0.1).astype(F)
+        cl.worker.grad_flat[0][:n].copy_(torch.from_numpy(g))
+        torch.cuda.synchronize()
+        cl.round(psx.MODE_SUM)                       # one ordinary round first
+        ref.round(g[None, :], o.SUM)
+        try:
+            graph = cl.capture_round(psx.MODE_SUM)
+        except Exception as exc:                     # capture of stream memops unsupported
+            pytest.skip("stream capture of the round failed: %s" % str(exc)[:200])
+        for _ in range(5):
+            with torch.cuda.stream(cl.worker_stream):
+                graph.replay()
+            ref.round(g[None, :], o.SUM)
+        cl.round(psx.MODE_SUM)                       # and ordinary rounds still work after
+        ref.round(g[None, :], o.SUM)
+        cl.barrier()
+        got = cl.worker.param_flat[0][:n].cpu().numpy()
+        assert_bits_equal(got, ref.var, "params after replays")
+        st = next(iter(cl.servers.values())).shard.state()
+        assert st["global_step"] == ref.step == 7
+    finally:
+        cl.close()

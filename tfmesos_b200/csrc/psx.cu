@@ -333,6 +333,7 @@ int launch_copy(void *dst, int dst_t, const void *src, int src_t, uint64_t n, in
 struct ApplyRange {
     size_t off, n;
     int finish;
+    unsigned int consume = 0;   // arrivals to take off the counter (counted rendez-vous)
 };
 
 template <int OPT, int MODE, bool SCATTER, typename SRC>
@@ -343,12 +344,12 @@ void launch_apply_t(Shard *s, SRC src, int count, const PeerSet &peers, cudaStre
     const int grid = grid_for(n4 ? n4 : 1, kApplyThreads, s->sm_count, 3);
     k_apply<OPT, MODE, SCATTER, SRC><<<grid, kApplyThreads, 0, st>>>(
         s->hdr(), (float4 *)(s->var() + r.off), (float4 *)(s->m() + r.off),
-        (float4 *)(s->v() + r.off), src, count, n4, peers, r.finish);
+        (float4 *)(s->v() + r.off), src, count, n4, peers, r.finish, r.consume);
 }
 
 template <bool SCATTER, typename SRC>
 int launch_apply(Shard *s, int mode, SRC src, int count, const PeerSet &peers, cudaStream_t st,
-                 ApplyRange r = ApplyRange{0, 0, 1})
+                 ApplyRange r = ApplyRange{0, 0, 1, 0})
 {
     if (r.n == 0 && r.off == 0) r.n = s->lay.nelem_pad;
 #define PSX_AP(O, M) launch_apply_t<O, M, SCATTER, SRC>(s, src, count, peers, st, r)
@@ -676,7 +677,7 @@ int psx_apply_range(uint64_t id, int mode, int first_slot, int count, uint64_t e
     PeerSet peers;
     memset(&peers, 0, sizeof(peers));
     fill_mirrors(s, &peers);
-    const ApplyRange r{(size_t)elem_off, (size_t)elem_n, finish ? 1 : 0};
+    const ApplyRange r{(size_t)elem_off, (size_t)elem_n, finish ? 1 : 0, 0};
     if (s->lay.wire == PSX_F32) {
         SlotSrc<float> src{(const float *)s->slot(0) + elem_off, (size_t)s->lay.nelem_pad, first_slot};
         return launch_apply<false>(s, mode, src, count, peers, (cudaStream_t)stream, r);
@@ -688,6 +689,27 @@ int psx_apply_range(uint64_t id, int mode, int first_slot, int count, uint64_t e
 int psx_apply(uint64_t id, int mode, int first_slot, int count, uint32_t wait_seq, void *stream)
 {
     return psx_apply_range(id, mode, first_slot, count, 0, 0, 1, wait_seq, stream);
+}
+
+int psx_apply_counted(uint64_t id, int mode, int first_slot, int count, void *stream)
+{
+    Shard *s = find(g_shards, id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    int rc = check_range(first_slot, count, s->lay.n_slots);
+    if (rc) return rc;
+    PSX_DEVICE(s->device);
+    rc = stream_wait_geq(stream, &s->hdr()->arrivals, (uint32_t)count);
+    if (rc) return rc;
+    PeerSet peers;
+    memset(&peers, 0, sizeof(peers));
+    fill_mirrors(s, &peers);
+    const ApplyRange r{0, (size_t)s->lay.nelem_pad, 1, (unsigned int)count};
+    if (s->lay.wire == PSX_F32) {
+        SlotSrc<float> src{(const float *)s->slot(0), (size_t)s->lay.nelem_pad, first_slot};
+        return launch_apply<false>(s, mode, src, count, peers, (cudaStream_t)stream, r);
+    }
+    SlotSrc<__nv_bfloat16> src{(const __nv_bfloat16 *)s->slot(0), (size_t)s->lay.nelem_pad, first_slot};
+    return launch_apply<false>(s, mode, src, count, peers, (cudaStream_t)stream, r);
 }
 
 int psx_wait_slots(uint64_t id, int first_slot, int count, uint32_t wait_seq, void *stream)
@@ -830,13 +852,20 @@ int psx_pull(uint64_t client_id, void *param_dev, uint64_t off, uint64_t n, int 
                        nullptr, 0, (cudaStream_t)stream);
 }
 
-int psx_signal_many(const uint64_t *client_ids, int n, uint32_t seq, void *stream)
+static int signal_impl(const uint64_t *client_ids, int n, uint32_t seq, uint64_t mailbox_id,
+                       uint32_t consume, void *stream)
 {
     if (!client_ids || n < 1 || n > kMaxSignal)
         return fail(PSX_EINVAL, "psx_signal_many takes 1..%d clients", kMaxSignal);
     SignalSet set;
     memset(&set, 0, sizeof(set));
     set.n = n;
+    if (mailbox_id) {
+        Mailbox *m = find(g_mailboxes, mailbox_id);
+        if (!m) return fail(PSX_EINVAL, "unknown mailbox id");
+        set.mailbox = m->counter;
+        set.consume = consume;
+    }
     int device = -1;
     for (int i = 0; i < n; ++i) {
         Client *c = find(g_clients, client_ids[i]);
@@ -852,9 +881,40 @@ int psx_signal_many(const uint64_t *client_ids, int n, uint32_t seq, void *strea
     return PSX_OK;
 }
 
+int psx_signal_many(const uint64_t *client_ids, int n, uint32_t seq, void *stream)
+{
+    return signal_impl(client_ids, n, seq, 0, 0, stream);
+}
+
+int psx_signal_counted(const uint64_t *client_ids, int n, uint32_t seq, uint64_t mailbox_id,
+                       uint32_t consume, void *stream)
+{
+    return signal_impl(client_ids, n, seq, mailbox_id, consume, stream);
+}
+
 int psx_signal(uint64_t client_id, uint32_t seq, void *stream)
 {
     return psx_signal_many(&client_id, 1, seq, stream);
+}
+
+int psx_mailbox_set(uint64_t id, uint32_t value)
+{
+    Mailbox *m = find(g_mailboxes, id);
+    if (!m) return fail(PSX_EINVAL, "unknown mailbox id");
+    PSX_DEVICE(m->device);
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(m->counter, &value, sizeof(value), cudaMemcpyHostToDevice));
+    return PSX_OK;
+}
+
+int psx_mailbox_consume(uint64_t id, uint32_t n, void *stream)
+{
+    Mailbox *m = find(g_mailboxes, id);
+    if (!m) return fail(PSX_EINVAL, "unknown mailbox id");
+    PSX_DEVICE(m->device);
+    k_consume<<<1, 1, 0, (cudaStream_t)stream>>>(m->counter, n);
+    LAUNCH_CHECK();
+    return PSX_OK;
 }
 
 int psx_wait_arrivals(uint64_t shard_id, uint32_t target, void *stream)
@@ -1178,7 +1238,8 @@ int psx_round_bind(uint64_t shard_id, int slot, const void *grad_buf_handle,
     return PSX_OK;
 }
 
-int psx_round(uint64_t shard_id, int mode, int first_slot, int count, uint32_t wait_seq, void *stream)
+static int round_impl(uint64_t shard_id, int mode, int first_slot, int count, uint32_t wait_seq,
+                      int counted, void *stream)
 {
     Shard *s = find(g_shards, shard_id);
     if (!s) return fail(PSX_EINVAL, "unknown shard id");
@@ -1197,16 +1258,31 @@ int psx_round(uint64_t shard_id, int mode, int first_slot, int count, uint32_t w
         if (s->bound[c].valid)
             peers.param[peers.n_param++] = s->bound[c].param.base + s->bound[c].elem_off * wb;
     PSX_DEVICE(s->device);
-    // slot flags exist for all PSX_MAX_SLOTS slots, whether or not the shard has
-    // landing slots (psx_round needs none)
-    rc = wait_slots(s, first_slot, count, wait_seq, stream);
+    if (counted) {
+        rc = stream_wait_geq(stream, &s->hdr()->arrivals, (uint32_t)count);
+    } else {
+        // slot flags exist for all PSX_MAX_SLOTS slots, whether or not the shard has
+        // landing slots (psx_round needs none)
+        rc = wait_slots(s, first_slot, count, wait_seq, stream);
+    }
     if (rc) return rc;
+    const ApplyRange r{0, (size_t)s->lay.nelem_pad, 1, counted ? (unsigned int)count : 0u};
     if (s->lay.wire == PSX_F32) {
         PeerSrc<float> src{peers, first_slot};
-        return launch_apply<true>(s, mode, src, count, peers, (cudaStream_t)stream);
+        return launch_apply<true>(s, mode, src, count, peers, (cudaStream_t)stream, r);
     }
     PeerSrc<__nv_bfloat16> src{peers, first_slot};
-    return launch_apply<true>(s, mode, src, count, peers, (cudaStream_t)stream);
+    return launch_apply<true>(s, mode, src, count, peers, (cudaStream_t)stream, r);
+}
+
+int psx_round(uint64_t shard_id, int mode, int first_slot, int count, uint32_t wait_seq, void *stream)
+{
+    return round_impl(shard_id, mode, first_slot, count, wait_seq, 0, stream);
+}
+
+int psx_round_counted(uint64_t shard_id, int mode, int first_slot, int count, void *stream)
+{
+    return round_impl(shard_id, mode, first_slot, count, 0, 1, stream);
 }
 
 int psx_batch(const psx_op *ops, int n_ops, int *failed_index)
@@ -1226,6 +1302,13 @@ int psx_batch(const psx_op *ops, int n_ops, int *failed_index)
         case PSX_OP_SIGNAL_MANY: rc = psx_signal_many((const uint64_t *)o.ptr, (int)o.n, o.seq, o.stream); break;
         case PSX_OP_WAIT_ARRIVALS: rc = psx_wait_arrivals(o.id, o.seq * (uint32_t)o.c, o.stream); break;
         case PSX_OP_WAIT_MAILBOX: rc = psx_wait_mailbox(o.id, o.seq * (uint32_t)o.c, o.stream); break;
+        case PSX_OP_ROUND_COUNTED: rc = psx_round_counted(o.id, o.a, o.b, o.c, o.stream); break;
+        case PSX_OP_APPLY_COUNTED: rc = psx_apply_counted(o.id, o.a, o.b, o.c, o.stream); break;
+        case PSX_OP_SIGNAL_COUNTED:
+            rc = psx_signal_counted((const uint64_t *)o.ptr, (int)o.n, o.seq, o.id, (uint32_t)o.c, o.stream);
+            break;
+        case PSX_OP_MAILBOX_WAIT: rc = psx_wait_mailbox(o.id, (uint32_t)o.c, o.stream); break;
+        case PSX_OP_MAILBOX_CONSUME: rc = psx_mailbox_consume(o.id, (uint32_t)o.c, o.stream); break;
         default: rc = fail(PSX_EINVAL, "batch op %d: unknown opcode %d", i, o.op);
         }
         if (rc) {

@@ -370,6 +370,9 @@ k_list_ldst(const ListChunk *__restrict__ chunks, int n_chunks, char *shard_base
     }
 }
 
+// one thread: take `n` completions off a worker's mailbox (counted rendez-vous)
+__global__ void k_consume(unsigned int *counter, unsigned int n) { atomicSub(counter, n); }
+
 // "my gradients for round seq are in place", to up to kMaxSignal shards in ONE
 // launch: thread i publishes slot flag i and bumps that shard's arrival counter
 constexpr int kMaxSignal = 64;
@@ -377,9 +380,12 @@ struct SignalSet {
     unsigned int *flag[kMaxSignal];
     unsigned int *arrivals[kMaxSignal];
     int n;
+    unsigned int *mailbox;      // optional: this worker's mailbox ...
+    unsigned int consume;       // ... from which last round's completions are taken first
 };
 __global__ void k_signal(SignalSet set, unsigned int seq)
 {
+    if (set.mailbox != nullptr && threadIdx.x == 0) atomicSub(set.mailbox, set.consume);
     if ((int)threadIdx.x < set.n) {
         __threadfence_system();
         publish_store(set.flag[threadIdx.x], seq);
@@ -476,8 +482,15 @@ template <typename W> struct WireOf<PeerSrc<W>> { using type = W; };
 template <int OPT, int MODE, bool SCATTER, typename SRC>
 __global__ void __launch_bounds__(kApplyThreads, PSX_APPLY_MIN_CTAS)
 k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restrict__ mom,
-        float4 *__restrict__ vel, SRC src, int count, size_t n4, PeerSet peers, int finish)
+        float4 *__restrict__ vel, SRC src, int count, size_t n4, PeerSet peers, int finish,
+        unsigned int consume)
 {
+    // counted rendez-vous: the stream waited for arrivals >= consume right before
+    // this launch; take them off the counter so the next round waits for the same
+    // constant again (that is what makes a round replayable from a CUDA graph).
+    // Next-round arrivals cannot come before this kernel's END (workers start their
+    // next round only after it has bumped their mailbox), so this cannot race them.
+    if (consume != 0 && blockIdx.x == 0 && threadIdx.x == 0) atomicSub(&h->arrivals, consume);
     __shared__ float s_alpha[PSX_MAX_SLOTS];
     const float lr = h->lr, b1 = h->b1, b2 = h->b2, eps = h->eps;
     const float omb1 = __fsub_rn(1.0f, b1);

@@ -423,6 +423,9 @@ class TorchrunCluster(object):
             for widx, h in boxes.items():
                 ps.shard.register_mailbox(widx, h)
         self.n_shards = len(self.topo.shards)
+        # counted rendez-vous invariant: between rounds a worker's mailbox holds
+        # n_shards (the completions of the previous round, not yet consumed)
+        self.mailbox.set(self.n_shards)
         if fused:
             bufs = self._merge({self.rank: self.worker.buffer_handles()})
             for key, ps in self.servers.items():
@@ -463,7 +466,10 @@ class TorchrunCluster(object):
                 ps.shard.set_values(psx.VAR, flat[lo - off:hi - off], lo - spec.off)
 
     def _build_batch(self, mode):
-        """The round as one psx_batch: the same ops round() issues one by one."""
+        """The round as one psx_batch.  Counted rendez-vous: every wait compares
+        with a constant (arrivals >= n_workers, mailbox >= n_shards) and the waiter
+        consumes what it waited for, so the sequence is identical every round --
+        replayable from a CUDA graph (capture_round)."""
         import ctypes
         ws, pss, wk = self.worker_stream, self.ps_stream, self.worker
         ops = []
@@ -471,19 +477,22 @@ class TorchrunCluster(object):
         if self.fused:
             ids = (ctypes.c_uint64 * len(wk.clients))(*[c.id for c in wk.clients.values()])
             keep.append(ids)
-            ops.append(dict(op=psx.OP_SIGNAL_MANY, ptr=ctypes.addressof(ids), n=len(ids),
-                            stream=ws))
+            ops.append(dict(op=psx.OP_SIGNAL_COUNTED, ptr=ctypes.addressof(ids), n=len(ids),
+                            id=self.mailbox.id, c=self.n_shards, stream=ws))
         else:
+            ops.append(dict(op=psx.OP_MAILBOX_CONSUME, id=self.mailbox.id, c=self.n_shards,
+                            stream=ws, uses_seq=False))
             for sp in wk.order:
                 g = wk.grad_flat[sp.task]
                 ops.append(dict(op=psx.OP_PUSH, id=wk.clients[sp.key].id,
                                 ptr=g.data_ptr() + sp.off * g.element_size(), off=0,
                                 n=sp.nelem, a=wk.wire, stream=ws))
         for ps in self.servers.values():
-            ops.append(dict(op=psx.OP_WAIT_ARRIVALS, id=ps.shard.id, c=self.world, stream=pss))
-            ops.append(dict(op=psx.OP_ROUND if self.fused else psx.OP_APPLY, id=ps.shard.id,
-                            a=mode, b=0, c=self.world, stream=pss, uses_seq=False))
-        ops.append(dict(op=psx.OP_WAIT_MAILBOX, id=self.mailbox.id, c=self.n_shards, stream=ws))
+            ops.append(dict(op=psx.OP_ROUND_COUNTED if self.fused else psx.OP_APPLY_COUNTED,
+                            id=ps.shard.id, a=mode, b=0, c=self.world, stream=pss,
+                            uses_seq=False))
+        ops.append(dict(op=psx.OP_MAILBOX_WAIT, id=self.mailbox.id, c=self.n_shards, stream=ws,
+                        uses_seq=False))
         if not self.fused:
             for sp in wk.order:
                 p = wk.param_flat[sp.task]
@@ -492,6 +501,12 @@ class TorchrunCluster(object):
                                 n=sp.nelem, a=wk.wire, stream=ws, uses_seq=False))
         batch = psx.Batch(ops)
         batch.keep = keep
+        return batch
+
+    def _batch(self, mode):
+        batch = self._batches.get(mode)
+        if batch is None:
+            batch = self._batches[mode] = self._build_batch(mode)
         return batch
 
     def round(self, mode, timer=None):
@@ -503,30 +518,48 @@ class TorchrunCluster(object):
         whole round is ONE call into libpsx (psx_batch)."""
         self.seq += 1
         if timer is None:
-            batch = self._batches.get(mode)
-            if batch is None:
-                batch = self._batches[mode] = self._build_batch(mode)
-            batch.run(self.seq)
+            self._batch(mode).run(self.seq)
             return
         ws, pss, wk = self.worker_stream, self.ps_stream, self.worker
         if self.fused:
-            psx.signal_many(list(wk.clients.values()), self.seq, ws)
+            psx.signal_counted(list(wk.clients.values()), self.seq, self.mailbox,
+                               self.n_shards, ws)
         else:
+            self.mailbox.consume(self.n_shards, ws)
             wk.push(self.seq, ws)
         for ps in self.servers.values():
-            ps.shard.wait_arrivals(self.seq * self.world, pss)
             timed = ps is self.dominant
-            if timed:
+            if timed:       # bracket the kernel alone: do the counted wait by hand first
+                ps.shard.wait_arrivals(self.world, pss)
                 timer.start(pss)
             if self.fused:
-                ps.round(mode, 0, pss)
+                ps.shard.round_counted(mode, 0, self.world, pss)
             else:
-                ps.apply(mode, 0, pss)
+                ps.shard.apply_counted(mode, 0, self.world, pss)
             if timed:
                 timer.stop(pss)
-        self.mailbox.wait(self.seq * self.n_shards, ws)
+        self.mailbox.wait(self.n_shards, ws)
         if not self.fused:
             wk.pull(0, ws)
+
+    def capture_round(self, mode, pre=None):
+        """A CUDA graph holding ``pre()`` (e.g. the worker's forward/backward)
+        followed by one PS round; ``graph.replay()`` then IS a training step.
+        Launch-bound steps (the 318 KB MNIST model) are host-call bound otherwise."""
+        import torch
+        ws, pss = self.worker_stream, self.ps_stream
+        batch = self._batch(mode)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=ws):
+            if pre is not None:
+                pre()
+            pss.wait_stream(ws)            # pull the PS stream into the capture
+            # any non-zero sequence number: it only stamps the (unused here) slot
+            # flags -- zero would mean "publish nothing"
+            batch.run(1)
+            ws.wait_stream(pss)            # and join it again
+        return graph
 
     def round_host(self, mode):
         """The same round from HOST buffers, software-pipelined over the shards:
@@ -545,6 +578,7 @@ class TorchrunCluster(object):
         self.seq += 1
         seq = self.seq
         hs.wait_stream(ws)                 # last round's pushes have read grad_flat
+        self.mailbox.consume(self.n_shards, ws)   # counted rendez-vous: start from zero
         # same shard order on every rank here: shard i's pull sits behind shard
         # i+1's push on one stream, so a per-rank rotation would make the ranks
         # wait on each other in a cycle (and PCIe, not NVLink incast, is the limit)
@@ -561,8 +595,7 @@ class TorchrunCluster(object):
                 wk.clients[sp.key].push(g.data_ptr(), sp.nelem, 0, wk.wire, seq, ws)
                 ps = self.servers.get(sp.key)
                 if ps is not None:
-                    ps.shard.wait_arrivals(seq * self.world, pss)
-                    ps.apply(mode, 0, pss)
+                    ps.shard.apply_counted(mode, 0, self.world, pss)
             if i >= 1:
                 sp = shards[i - 1]
                 p = wk.param_flat[sp.task][sp.off:sp.off + sp.nelem]
@@ -572,6 +605,7 @@ class TorchrunCluster(object):
                 ds.wait_event(ev)
                 with torch.cuda.stream(ds):
                     st.param[sp.task][sp.off:sp.off + sp.nelem].copy_(p, non_blocking=True)
+        self.mailbox.wait(self.n_shards, ws)   # every shard applied (invariant restored)
         ws.wait_stream(ds)                 # the step ends when the host has the parameters
 
     def close(self):

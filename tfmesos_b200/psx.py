@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # TFMESOS_PSX_LIB selects another build of the same ABI (kernel A/B experiments)
 LIB_PATH = os.environ.get("TFMESOS_PSX_LIB") or os.path.join(HERE, "lib", "libpsx.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 OPT_SGD, OPT_ADAM = 0, 1
 MODE_ASYNC_ORDERED, MODE_SUM, MODE_SYNC_MEAN = 0, 1, 2
 F32, BF16 = 0, 1
@@ -28,7 +28,8 @@ _vp = ctypes.c_void_p
 _fp = ctypes.POINTER(ctypes.c_float)
 
 (OP_PUSH, OP_PULL, OP_APPLY, OP_ROUND, OP_SIGNAL, OP_WAIT_APPLIED, OP_WAIT_SLOTS,
- OP_SIGNAL_MANY, OP_WAIT_ARRIVALS, OP_WAIT_MAILBOX) = range(1, 11)
+ OP_SIGNAL_MANY, OP_WAIT_ARRIVALS, OP_WAIT_MAILBOX, OP_ROUND_COUNTED, OP_APPLY_COUNTED,
+ OP_SIGNAL_COUNTED, OP_MAILBOX_WAIT, OP_MAILBOX_CONSUME) = range(1, 16)
 
 
 class Op(ctypes.Structure):
@@ -76,6 +77,11 @@ SIGNATURES = {
     "psx_wait_applied": (_i32, [_u64, _u32, _vp]),
     "psx_round": (_i32, [_u64, _i32, _i32, _i32, _u32, _vp]),
     "psx_signal_many": (_i32, [ctypes.POINTER(_u64), _i32, _u32, _vp]),
+    "psx_round_counted": (_i32, [_u64, _i32, _i32, _i32, _vp]),
+    "psx_apply_counted": (_i32, [_u64, _i32, _i32, _i32, _vp]),
+    "psx_signal_counted": (_i32, [ctypes.POINTER(_u64), _i32, _u32, _u64, _u32, _vp]),
+    "psx_mailbox_consume": (_i32, [_u64, _u32, _vp]),
+    "psx_mailbox_set": (_i32, [_u64, _u32]),
     "psx_wait_arrivals": (_i32, [_u64, _u32, _vp]),
     "psx_mailbox_create": (_i32, [_i32, ctypes.POINTER(_u64)]),
     "psx_mailbox_export": (_i32, [_u64, _vp]),
@@ -239,6 +245,14 @@ class Shard(object):
         _check(lib().psx_round(self.id, int(mode), int(first_slot), int(count),
                                int(wait_seq), _stream_ptr(stream)))
 
+    def round_counted(self, mode, first_slot, count, stream=None):
+        _check(lib().psx_round_counted(self.id, int(mode), int(first_slot), int(count),
+                                       _stream_ptr(stream)))
+
+    def apply_counted(self, mode, first_slot, count, stream=None):
+        _check(lib().psx_apply_counted(self.id, int(mode), int(first_slot), int(count),
+                                       _stream_ptr(stream)))
+
 
 class Client(object):
     """Worker-side attachment to a shard (psx_shard_open)."""
@@ -293,6 +307,12 @@ class Mailbox(object):
     def wait(self, target, stream=None):
         _check(lib().psx_wait_mailbox(self.id, int(target) & 0xFFFFFFFF, _stream_ptr(stream)))
 
+    def set(self, value):
+        _check(lib().psx_mailbox_set(self.id, int(value)))
+
+    def consume(self, n, stream=None):
+        _check(lib().psx_mailbox_consume(self.id, int(n), _stream_ptr(stream)))
+
     def destroy(self):
         if self.id:
             _check(lib().psx_mailbox_destroy(self.id))
@@ -302,6 +322,12 @@ class Mailbox(object):
 def signal_many(clients, seq, stream=None):
     ids = (_u64 * len(clients))(*[c.id for c in clients])
     _check(lib().psx_signal_many(ids, len(clients), int(seq), _stream_ptr(stream)))
+
+
+def signal_counted(clients, seq, mailbox, consume, stream=None):
+    ids = (_u64 * len(clients))(*[c.id for c in clients])
+    _check(lib().psx_signal_counted(ids, len(clients), int(seq), mailbox.id, int(consume),
+                                    _stream_ptr(stream)))
 
 
 class TensorList(object):
