@@ -66,3 +66,38 @@ def test_compute_calls_fail_loudly_without_a_gpu():
 def test_bad_handles_are_rejected():
     with pytest.raises(RuntimeError, match="not a psx handle"):
         psx.Client(b"\0" * psx.HANDLE_BYTES, 0, 0)
+
+
+def test_batch_struct_layout_matches_header():
+    """struct psx_op in include/psx.h <-> ctypes mirror: same field order and size."""
+    text = open(os.path.join(ROOT, "include", "psx.h")).read()
+    body = re.search(r"typedef struct psx_op \{(.*?)\} psx_op;", text, re.S).group(1)
+    names = re.findall(r"\b(?:\*?)(\w+)(?:,|;)", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
+    names = [n for n in names if n not in ("int32_t", "uint64_t", "uint32_t", "void")]
+    assert names == [f[0] for f in psx.Op._fields_]
+    assert ctypes.sizeof(psx.Op) == 16 + 24 + 16 + 8          # 4 x i32, 3 x u64, 2 ptr, 2 x u32
+    consts = dict(re.findall(r"#define (PSX_OP_[A-Z_]+) (\d+)", text))
+    for name, val in consts.items():
+        assert getattr(psx, name[4:]) == int(val), name
+
+
+def test_batch_reports_the_failing_op_without_touching_cuda():
+    b = psx.Batch([dict(op=psx.OP_WAIT_APPLIED, id=12345, uses_seq=False, stream=0),
+                   dict(op=99, stream=0)])
+    with pytest.raises(RuntimeError, match="batch op 0 failed"):
+        b.run(1)
+    b2 = psx.Batch([dict(op=99, stream=0)])
+    with pytest.raises(RuntimeError, match="unknown opcode 99"):
+        b2.run(1)
+
+
+def test_argument_validation_that_needs_no_device():
+    lib = psx.lib()
+    ids = (ctypes.c_uint64 * 1)(7)
+    assert lib.psx_signal_many(ids, 0, 1, None) == -1                  # PSX_EINVAL: n out of range
+    assert lib.psx_signal_many(ids, 1, 1, None) == -1                  # unknown client id
+    assert b"unknown client id" in lib.psx_last_error()
+    assert lib.psx_wait_mailbox(424242, 1, None) == -1
+    assert lib.psx_shard_destroy(424242) == -1
+    out = ctypes.c_uint64(0)
+    assert lib.psx_list_create(424242, None, None, None, 1, ctypes.byref(out)) == -1
