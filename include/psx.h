@@ -158,7 +158,7 @@ int psx_shard_register_client(uint64_t shard_id, int slot, const void *client_ha
 /* PUSH: copy n gradient elements grad_dev[0..n) into elements [off, off+n) of
  * this client's slot in the PS shard's HBM (vectorised stores, straight over
  * NVLink when the shard is on another GPU), then publish `seq` in the slot's
- * flag word (st.release.sys) unless seq == 0.  src_dtype: type of grad_dev.
+ * flag word (fence.sys + system-scope store) unless seq == 0.  src_dtype: type of grad_dev.
  * Replaces: gradient _Send/_Recv worker->ps, one RecvTensor per variable. */
 int psx_push(uint64_t client_id, const void *grad_dev, uint64_t off, uint64_t n,
              int src_dtype, uint32_t seq, void *stream);
@@ -198,7 +198,7 @@ int psx_buffer_destroy(uint64_t id);
 int psx_round_bind(uint64_t shard_id, int slot, const void *grad_buf_handle,
                    const void *param_buf_handle, uint64_t elem_off);
 
-/* Worker: "my bound gradient buffer holds round `seq`" (release store into the
+/* Worker: "my bound gradient buffer holds round `seq`" (fence.sys + system-scope store into the
  * shard's slot flag).  Worker: wait until apply round `seq` is done. */
 int psx_signal(uint64_t client_id, uint32_t seq, void *stream);
 int psx_wait_applied(uint64_t client_id, uint32_t seq, void *stream);

@@ -11,7 +11,7 @@
 //             in the WORKER's HBM (push ticket, mirror of apply_seq).
 //   buffer  = exportable worker staging (gradients / parameters) for psx_round.
 // Waiting never holds an SM: consumers wait with cuStreamWaitValue32 on a flag
-// in their OWN HBM that the producer's kernel release-stores remotely.
+// in their OWN HBM that the producer's kernel publishes remotely (fence.sys + store).
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <unistd.h>

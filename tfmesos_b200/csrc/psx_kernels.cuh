@@ -8,7 +8,7 @@
 //   * arithmetic spelled with __f*_rn intrinsics: one IEEE-754 rounding per
 //     operation, never contracted to FMA, so results are bit-identical to the
 //     CPU restatement of TF 0.12's ApplyGradientDescent / ApplyAdam
-//   * completion published with a last-CTA ticket + st.release.sys flag so the
+//   * completion published with a last-CTA ticket + fence.sys + system-scope flag store so the
 //     consumer (another GPU / another process) can wait with a stream memop
 //     instead of a spinning kernel.
 #pragma once
@@ -137,7 +137,7 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 // may live in another GPU's HBM).  bar.sync, then thread 0: fence at GPU scope
 // (orders every write of this CTA before its ticket, cumulatively), ticket; the
 // CTA that draws the last ticket has thereby observed all the others, issues ONE
-// system-scope fence and release-stores the flag.  (A MEMBAR.SYS costs ~3 us;
+// system-scope fence and stores the flag(s).  (A MEMBAR.SYS costs ~3 us;
 // paying it once per kernel instead of once per CTA is what keeps 300 KB
 // MNIST-sized rounds in the 10 us range -- profiles/r01.)
 __device__ __forceinline__ bool last_cta(unsigned int *ticket)
