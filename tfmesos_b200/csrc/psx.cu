@@ -537,6 +537,7 @@ int psx_shard_set_hyper(uint64_t id, const float *hyper)
     Shard *s = find(g_shards, id);
     if (!s || !hyper) return fail(PSX_EINVAL, "unknown shard id or null hyper");
     PSX_DEVICE(s->device);
+    CU_TRY(cudaDeviceSynchronize());   // not under a running apply
     CU_TRY(cudaMemcpy(&s->hdr()->lr, hyper, 4 * sizeof(float), cudaMemcpyHostToDevice));
     return PSX_OK;
 }
@@ -566,6 +567,9 @@ int psx_set_values(uint64_t id, int which, const float *host, uint64_t off, uint
     if (rc) return rc;
     if (n == 0) return PSX_OK;
     PSX_DEVICE(s->device);
+    // synchronous by contract: kernels on non-blocking streams are not ordered
+    // against the legacy stream's memcpy, so drain the device first
+    CU_TRY(cudaDeviceSynchronize());
     if (dt == PSX_F32) {
         CU_TRY(cudaMemcpy(base + off * 4, host, n * 4, cudaMemcpyHostToDevice));
     } else {  // stage f32 on the device, cast with the push kernel
