@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define PSX_ABI_VERSION 8
+#define PSX_ABI_VERSION 9
 
 /* error codes */
 #define PSX_OK 0
@@ -247,6 +247,25 @@ int psx_mailbox_set(uint64_t id, uint32_t value);
  * staging copy.  Waits like psx_apply. */
 int psx_round(uint64_t shard_id, int mode, int first_slot, int count, uint32_t wait_seq,
               void *stream);
+
+/* --------------------------------- NVSwitch multicast (NVLS), experimental --- */
+
+/* Single-process multicast buffers: one allocation per listed GPU, all bound to
+ * one multicast object.  psx_mc_broadcast stores a device array into EVERY GPU's
+ * copy with multimem.st (the broadcast-back leg of a pull); psx_mc_reduce reads
+ * the SUM over all copies with multimem.ld_reduce (the switch adds -- its order
+ * is not the slot order, so this is a tolerance-checked mode).  `member` indexes
+ * the device list given at creation; ranges are 16-byte granular.  Measured on 2
+ * GPUs only; psx_round does not use them. */
+int psx_nvls_supported(int device, int *out);
+int psx_mc_create(const int *devices, int n, uint64_t nbytes, uint64_t *out_id);
+int psx_mc_destroy(uint64_t id);
+int psx_mc_ptrs(uint64_t id, int member, void **out_unicast, void **out_multicast,
+                uint64_t *out_size);
+int psx_mc_broadcast(uint64_t id, int member, const void *src_dev, uint64_t off_bytes,
+                     uint64_t nbytes, void *stream);
+int psx_mc_reduce(uint64_t id, int member, void *dst_dev, uint64_t off_bytes, uint64_t nbytes,
+                  void *stream);
 
 /* ------------------------------------------------------------- batching --- */
 

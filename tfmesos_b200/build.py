@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "psx.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "psx_kernels.cuh"),
+        os.path.join(HERE, "csrc", "psx_nvls.cuh"),
         os.path.join(ROOT, "include", "psx.h")]
 OUT = os.path.join(HERE, "lib", "libpsx.so")
 

@@ -1332,3 +1332,5 @@ int psx_copy(int device, void *dst, const void *src, uint64_t nbytes, void *stre
 }
 
 }  // extern "C"
+
+#include "psx_nvls.cuh"

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # TFMESOS_PSX_LIB selects another build of the same ABI (kernel A/B experiments)
 LIB_PATH = os.environ.get("TFMESOS_PSX_LIB") or os.path.join(HERE, "lib", "libpsx.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 OPT_SGD, OPT_ADAM = 0, 1
 MODE_ASYNC_ORDERED, MODE_SUM, MODE_SYNC_MEAN = 0, 1, 2
 F32, BF16 = 0, 1
@@ -88,6 +88,13 @@ SIGNATURES = {
     "psx_mailbox_destroy": (_i32, [_u64]),
     "psx_shard_register_mailbox": (_i32, [_u64, _i32, _vp]),
     "psx_wait_mailbox": (_i32, [_u64, _u32, _vp]),
+    "psx_nvls_supported": (_i32, [_i32, ctypes.POINTER(_i32)]),
+    "psx_mc_create": (_i32, [ctypes.POINTER(_i32), _i32, _u64, ctypes.POINTER(_u64)]),
+    "psx_mc_destroy": (_i32, [_u64]),
+    "psx_mc_ptrs": (_i32, [_u64, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                           ctypes.POINTER(_u64)]),
+    "psx_mc_broadcast": (_i32, [_u64, _i32, _vp, _u64, _u64, _vp]),
+    "psx_mc_reduce": (_i32, [_u64, _i32, _vp, _u64, _u64, _vp]),
     "psx_batch": (_i32, [ctypes.POINTER(Op), _i32, ctypes.POINTER(_i32)]),
     "psx_launch_count": (_u64, []),
     "psx_shard_ptr": (_i32, [_u64, _i32, ctypes.POINTER(_vp)]),
@@ -387,6 +394,55 @@ class Buffer(object):
         import torch
         raw = torch.as_tensor(self, device="cuda:%d" % self.device)
         return raw.view(torch.float32 if dtype is None else dtype)
+
+
+def nvls_supported(device):
+    v = _i32(0)
+    _check(lib().psx_nvls_supported(int(device), ctypes.byref(v)))
+    return bool(v.value)
+
+
+class MulticastBuffer(object):
+    """One buffer per GPU bound to one NVSwitch multicast object (experimental)."""
+
+    def __init__(self, devices, nbytes):
+        arr = (_i32 * len(devices))(*devices)
+        mid = _u64(0)
+        _check(lib().psx_mc_create(arr, len(devices), int(nbytes), ctypes.byref(mid)))
+        self.id = mid.value
+        self.devices = list(devices)
+        self.nbytes = int(nbytes)
+
+    def ptrs(self, member):
+        uc, mc, size = _vp(0), _vp(0), _u64(0)
+        _check(lib().psx_mc_ptrs(self.id, int(member), ctypes.byref(uc), ctypes.byref(mc),
+                                 ctypes.byref(size)))
+        return uc.value, mc.value, size.value
+
+    def tensor(self, member):
+        """float32 torch view of this member's own (unicast) copy."""
+        import torch
+        uc, _, _ = self.ptrs(member)
+
+        class _View(object):
+            __cuda_array_interface__ = {"shape": (self.nbytes // 4,), "typestr": "<f4",
+                                        "data": (uc, False), "version": 2, "strides": None}
+        v = _View()
+        v.owner = self
+        return torch.as_tensor(v, device="cuda:%d" % self.devices[member])
+
+    def broadcast(self, member, src_ptr, nbytes, off=0, stream=None):
+        _check(lib().psx_mc_broadcast(self.id, int(member), src_ptr, int(off), int(nbytes),
+                                      _stream_ptr(stream)))
+
+    def reduce(self, member, dst_ptr, nbytes, off=0, stream=None):
+        _check(lib().psx_mc_reduce(self.id, int(member), dst_ptr, int(off), int(nbytes),
+                                   _stream_ptr(stream)))
+
+    def destroy(self):
+        if self.id:
+            _check(lib().psx_mc_destroy(self.id))
+            self.id = 0
 
 
 class Batch(object):
