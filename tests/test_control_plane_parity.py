@@ -177,3 +177,38 @@ def test_unplaceable_job_fails_loudly_instead_of_waiting_for_more_offers():
     with pytest.raises(RuntimeError, match="cannot place"):
         with tfmesos_b200.cluster([dict(name="worker", num=2, gpus=4096)], quiet=True):
             pass
+
+
+def test_local_spawner_pins_each_gpu_task_to_its_slice(monkeypatch, tmp_path):
+    """The local driver offers the GPUs named by CUDA_VISIBLE_DEVICES as a SET;
+    first-fit hands ps tasks (gpus=0) nothing and each worker one ordinal, which
+    the child sees as ITS CUDA_VISIBLE_DEVICES (no GPU needed to check this)."""
+    import time
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "4,5,6")
+    child = tmp_path / "child.py"
+    child.write_text(
+        "import json, os, sys\n"
+        "open(os.path.join(sys.argv[1], os.environ['TFMESOS_JOB_NAME'] + '_' +\n"
+        "     os.environ['TFMESOS_TASK_INDEX'] + '.json'), 'w').write(\n"
+        "     json.dumps(os.environ.get('CUDA_VISIBLE_DEVICES')))\n")
+    cmd = "%s %s %s" % (sys.executable, child, tmp_path)
+    jobs = [dict(name="ps", num=1, cmd=cmd, gpus=0), dict(name="worker", num=3, cmd=cmd, gpus=1)]
+    with tfmesos_b200.cluster(jobs, quiet=True) as c:
+        slices = {(t.job_name, t.task_index): list(t.gpu_slice) for t in c.tasks.values()}
+        deadline = time.time() + 60
+        while not c.finished():
+            assert time.time() < deadline
+            time.sleep(0.05)
+        time.sleep(0.3)
+    assert slices == {("ps", 0): [], ("worker", 0): ["4"], ("worker", 1): ["5"],
+                      ("worker", 2): ["6"]}
+    seen = {fn[:-5]: json.load(open(tmp_path / fn)) for fn in os.listdir(tmp_path)
+            if fn.endswith(".json")}
+    assert seen == {"ps_0": "4,5,6", "worker_0": "4", "worker_1": "5", "worker_2": "6"}
+
+
+def test_local_spawner_refuses_more_gpu_tasks_than_gpus(monkeypatch):
+    monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "0")
+    with pytest.raises(RuntimeError, match="cannot place worker:1"):
+        with tfmesos_b200.cluster([dict(name="worker", num=2, gpus=1, cmd="true")], quiet=True):
+            pass
