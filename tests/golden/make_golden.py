@@ -107,7 +107,9 @@ def run_replica_mode(rs, addict):
                     env[var.name] = var.value
                 env["PYTHONPATH"] = os.pathsep.join(
                     [STUBS, REF, env.get("PYTHONPATH", "")])
-                p = subprocess.Popen(ti.command.value, shell=True, env=env,
+                # neutral cwd: the repo root holds a `tfmesos` alias package that
+                # would shadow the reference for `python -m tfmesos.server`
+                p = subprocess.Popen(ti.command.value, shell=True, env=env, cwd=tmp,
                                      stdout=subprocess.DEVNULL,
                                      stderr=subprocess.DEVNULL)
                 procs.append((ti.task_id.value, p))
@@ -128,10 +130,17 @@ def run_replica_mode(rs, addict):
             pass
 
     rs.MesosSchedulerDriver = FakeDriver
+    hooks = os.path.join(tmp, "hooks.txt")
+    extra = {"initializer": "echo init >> %s" % hooks, "finalizer": "echo fin >> %s" % hooks}
     sched = rs.TFMesosScheduler([rs.Job(**j) for j in jobs], master="stub",
-                                quiet=True, extra_config={},
+                                quiet=True, extra_config=extra,
                                 forward_addresses=None)
+    # the reference's start() waits for ever if a task never registers
+    watchdog = threading.Timer(120, lambda: os._exit(3))
+    watchdog.daemon = True
+    watchdog.start()
     sched.start()
+    watchdog.cancel()
     names = {t.mesos_task_id: (t.job_name, t.task_index, t.addr)
              for t in sched.tasks.values()}
     addr_mask = {a: "<%s:%s>" % (j, i) for (j, i, a) in names.values()}
@@ -148,8 +157,14 @@ def run_replica_mode(rs, addict):
         sched.statusUpdate(None, upd)
     results["finished"] = sched.finished()
     results["job_finished"] = dict(sched.job_finished)
+    with open(hooks) as f:
+        lines = f.read().split()
+    # extra_config initializer / finalizer (server.py:68-70,106-109)
+    results["extra_config_hooks"] = {"init": lines.count("init"), "fin": lines.count("fin")}
     children = {}
     for fn in sorted(os.listdir(tmp)):
+        if not fn.endswith(".json"):
+            continue
         with open(os.path.join(tmp, fn)) as f:
             rec = json.load(f)
         rec["argv"] = [scenarios.mask_addr(a, addr_mask) for a in rec["argv"]]

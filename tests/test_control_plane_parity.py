@@ -108,7 +108,9 @@ def test_replica_mode_end_to_end_matches_reference():
            % (sys.executable, probe, tmp))
     jobs = [dict(name="ps", num=1, cmd=cmd), dict(name="worker", num=2, cmd=cmd)]
     import time
-    with tfmesos_b200.cluster(jobs, quiet=True) as c:
+    hooks = os.path.join(tmp, "hooks.txt")
+    extra = {"initializer": "echo init >> %s" % hooks, "finalizer": "echo fin >> %s" % hooks}
+    with tfmesos_b200.cluster(jobs, quiet=True, extra_config=extra) as c:
         names = {t.mesos_task_id: (t.job_name, t.task_index, t.addr)
                  for t in c.tasks.values()}
         targets = dict(c.targets)
@@ -123,8 +125,13 @@ def test_replica_mode_end_to_end_matches_reference():
     gold = GOLDEN["replica_mode"]
     assert {k: scenarios.mask_addr(v, addr_mask) for k, v in targets.items()} == gold["targets"]
     assert job_finished["worker"] == gold["job_finished"]["worker"]
+    lines = open(hooks).read().split()
+    # extra_config initializer / finalizer run once per task (server.py:68-70,106-109)
+    assert {"init": lines.count("init"), "fin": lines.count("fin")} == gold["extra_config_hooks"]
     children = {}
     for fn in sorted(os.listdir(tmp)):
+        if not fn.endswith(".json"):
+            continue
         rec = json.load(open(os.path.join(tmp, fn)))
         rec["argv"] = [scenarios.mask_addr(a, addr_mask) for a in rec["argv"]]
         rec["env"] = {k: scenarios.mask_addr(v, addr_mask) for k, v in rec["env"].items()}
