@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define PSX_ABI_VERSION 9
+#define PSX_ABI_VERSION 10
 
 /* error codes */
 #define PSX_OK 0
@@ -154,6 +154,11 @@ int psx_shard_close(uint64_t id);
  * worker's HBM so the worker's pull waits on local memory. */
 int psx_client_export(uint64_t client_id, void *out_handle);
 int psx_shard_register_client(uint64_t shard_id, int slot, const void *client_handle);
+/* Detach worker `slot` again: drains the shard's device, then unmaps the
+ * worker's client block, mailbox and bound buffers.  A worker asks its PS for
+ * this BEFORE psx_shard_close frees the block (a tf.Session closing,
+ * examples/mnist/mnist_replica.py:183-220: the PS keeps serving the others). */
+int psx_shard_unregister_client(uint64_t shard_id, int slot);
 
 /* PUSH: copy n gradient elements grad_dev[0..n) into elements [off, off+n) of
  * this client's slot in the PS shard's HBM (vectorised stores, straight over
@@ -266,6 +271,34 @@ int psx_mc_broadcast(uint64_t id, int member, const void *src_dev, uint64_t off_
                      uint64_t nbytes, void *stream);
 int psx_mc_reduce(uint64_t id, int member, void *dst_dev, uint64_t off_bytes, uint64_t nbytes,
                   void *stream);
+
+/* Multi-process form (the product runs one process per GPU): one MEMBER per
+ * (process, GPU).  The creator makes the multicast object for `n_devices`
+ * members and gets its POSIX file descriptor, which the host ships to the other
+ * processes over an AF_UNIX socket (SCM_RIGHTS -- the 128-byte blobs cannot carry
+ * descriptors); they psx_mcx_import it.  Every member then adds its device
+ * (psx_mcx_add_device), the host synchronises all members (barrier), and each
+ * psx_mcx_bind creates this GPU's VMM allocation, binds it at offset 0 of the
+ * object and maps it twice: at a unicast address (ordinary loads / stores) and,
+ * as part of the whole team, at the multicast address.
+ * Replaces the transport selection of tfmesos/scheduler.py:186 (protocol='grpc')
+ * for the PS round's gather and broadcast-back legs. */
+int psx_mcx_create(int device, int n_devices, uint64_t nbytes, int *out_fd, uint64_t *out_id);
+int psx_mcx_import(int device, int n_devices, uint64_t nbytes, int fd, uint64_t *out_id);
+int psx_mcx_add_device(uint64_t id);
+int psx_mcx_bind(uint64_t id, void **out_unicast, void **out_multicast, uint64_t *out_size);
+int psx_mcx_destroy(uint64_t id);
+
+/* NVLS form of psx_round_bind: the workers' gradient / parameter tensors live at
+ * byte offsets grad_off_bytes / param_off_bytes of every member's arena (same
+ * layout in all of them); the shard covers elements [elem_off, elem_off + padded
+ * nelem) of those tensors.  psx_round / psx_round_counted on a shard bound this
+ * way gather with ONE multimem.ld_reduce.add.v4.f32 per vector (the switch sums
+ * the n_members copies) and scatter with ONE multimem.st per vector; SUM and
+ * SYNC_MEAN only, f32 wire, count must equal n_members.  Chosen once at set-up
+ * (capability query psx_nvls_supported), never per call. */
+int psx_round_bind_mc(uint64_t shard_id, uint64_t mcx_id, uint64_t grad_off_bytes,
+                      uint64_t param_off_bytes, uint64_t elem_off, int n_members);
 
 /* ------------------------------------------------------------- batching --- */
 

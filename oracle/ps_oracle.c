@@ -41,7 +41,9 @@
  *   PSX_ORACLE_SYNC_MEAN      g = sum / (float)W           then one apply
  *                             (SyncReplicasOptimizer, mnist_replica.py:148-154)
  */
+#define _GNU_SOURCE
 #include <math.h>
+#include <sched.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <string.h>
@@ -226,16 +228,45 @@ typedef struct {
     int W, opt_adam, mode, part, parts;
     float lr, b1, b2, eps;
     const float *b1p, *b2p;
+    int init;                 /* 1: first-touch + fill instead of a round */
 } cpu_ps_job;
 
-static void *cpu_ps_part(void *arg)
+/* deterministic fill values (exact integer hash -> (-0.01, 0.01)) */
+static float synth(size_t i, unsigned seed)
 {
-    cpu_ps_job *j = (cpu_ps_job *)arg;
+    uint64_t h = ((uint64_t)i * 2654435761ull + (uint64_t)seed * 40503ull + 12345ull) & 0xFFFFFFull;
+    return ((float)h / 16777216.0f - 0.5f) * 0.02f;
+}
+
+static void cpu_ps_part(cpu_ps_job *j)
+{
     size_t lo, hi;
     range_of(j->n, j->part, j->parts, &lo, &hi);
     size_t cnt = hi - lo;
     if (cnt == 0)
-        return NULL;
+        return;
+    if (j->init) {
+        /* FIRST TOUCH by the thread that will own this range in every round: the
+         * pages land on that thread's NUMA node (the arrays arrive untouched from
+         * the allocator), so placement -- and with it the measured number -- does
+         * not depend on which socket the launching thread happened to run on. */
+        for (size_t i = lo; i < hi; ++i) {
+            j->var[i] = synth(i, 7u) * 100.0f;
+            j->m[i] = 0.0f;
+            j->v[i] = 0.0f;
+            j->scratch[i] = 0.0f;
+        }
+        for (int w = 0; w < j->W; ++w) {
+            float *g = j->worker_grad[w], *p = j->worker_param[w];
+            float *s = j->slots + (size_t)w * j->stride;
+            for (size_t i = lo; i < hi; ++i) {
+                g[i] = synth(i, 100u + (unsigned)w);
+                p[i] = 0.0f;
+                s[i] = 0.0f;
+            }
+        }
+        return;
+    }
     /* PUSH: worker -> PS receive buffers */
     for (int w = 0; w < j->W; ++w)
         memcpy(j->slots + (size_t)w * j->stride + lo, j->worker_grad[w] + lo, cnt * 4);
@@ -261,10 +292,124 @@ static void *cpu_ps_part(void *arg)
     /* PULL: PS -> every worker */
     for (int w = 0; w < j->W; ++w)
         memcpy(j->worker_param[w] + lo, j->var + lo, cnt * 4);
-    return NULL;
 }
 
-/* threads <= 0: one per online core, but never less than 64 Ki elements each */
+/* ---- persistent thread pool ------------------------------------------------
+ * Created once (psx_oracle_pool_start); every round is two barrier crossings.
+ * Thread p is pinned to the p-th CPU of the affinity mask the process had when
+ * the pool started, so a range is always touched from the same core (and, with
+ * the first-touch initialisation above, from the socket its pages live on).
+ * (TF's PS runs its Eigen thread pool the same way: long-lived workers, one per
+ * core -- tfmesos/server.py:52-61 sizes it from the task's `cpus`.) */
+#define PSX_ORACLE_MAX_THREADS 512
+static struct {
+    int n;
+    pthread_t tid[PSX_ORACLE_MAX_THREADS];
+    int cpu[PSX_ORACLE_MAX_THREADS];
+    pthread_barrier_t start, done;
+    cpu_ps_job job;             /* template for the current round */
+    volatile int quit;
+} g_pool;
+
+static void *pool_main(void *arg)
+{
+    int p = (int)(intptr_t)arg;
+    if (g_pool.cpu[p] >= 0) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET(g_pool.cpu[p], &set);
+        pthread_setaffinity_np(pthread_self(), sizeof(set), &set);
+    }
+    for (;;) {
+        pthread_barrier_wait(&g_pool.start);
+        if (g_pool.quit)
+            return NULL;
+        cpu_ps_job j = g_pool.job;
+        j.part = p;
+        if (p < j.parts)
+            cpu_ps_part(&j);
+        pthread_barrier_wait(&g_pool.done);
+    }
+}
+
+int psx_oracle_pool_threads(void) { return g_pool.n; }
+
+/* threads <= 0: one per CPU this process may run on.  Returns the pool size. */
+int psx_oracle_pool_start(int threads)
+{
+    if (g_pool.n > 0)
+        return g_pool.n;
+    cpu_set_t allowed;
+    CPU_ZERO(&allowed);
+    int ncpu = 0, cpus[PSX_ORACLE_MAX_THREADS];
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+        for (int c = 0; c < CPU_SETSIZE && ncpu < PSX_ORACLE_MAX_THREADS; ++c)
+            if (CPU_ISSET(c, &allowed))
+                cpus[ncpu++] = c;
+    }
+    if (ncpu == 0) {
+        ncpu = psx_oracle_threads();
+        for (int c = 0; c < ncpu; ++c) cpus[c] = -1;
+    }
+    int n = threads > 0 ? threads : ncpu;
+    if (n > PSX_ORACLE_MAX_THREADS) n = PSX_ORACLE_MAX_THREADS;
+    g_pool.quit = 0;
+    pthread_barrier_init(&g_pool.start, NULL, (unsigned)n + 1);
+    pthread_barrier_init(&g_pool.done, NULL, (unsigned)n + 1);
+    for (int p = 0; p < n; ++p) {
+        g_pool.cpu[p] = cpus[p % ncpu];
+        if (pthread_create(&g_pool.tid[p], NULL, pool_main, (void *)(intptr_t)p) != 0) {
+            g_pool.n = p;       /* the barriers expect n+1: unusable, report failure */
+            return -3;
+        }
+    }
+    g_pool.n = n;
+    return n;
+}
+
+void psx_oracle_pool_stop(void)
+{
+    if (g_pool.n <= 0)
+        return;
+    g_pool.quit = 1;
+    pthread_barrier_wait(&g_pool.start);
+    for (int p = 0; p < g_pool.n; ++p)
+        pthread_join(g_pool.tid[p], NULL);
+    pthread_barrier_destroy(&g_pool.start);
+    pthread_barrier_destroy(&g_pool.done);
+    g_pool.n = 0;
+}
+
+static int pool_run(const cpu_ps_job *job)
+{
+    if (g_pool.n <= 0 && psx_oracle_pool_start(0) <= 0)
+        return -3;
+    g_pool.job = *job;
+    size_t cap = job->n / 65536 + 1;           /* never less than 64 Ki elements each */
+    g_pool.job.parts = (size_t)g_pool.n > cap ? (int)cap : g_pool.n;
+    pthread_barrier_wait(&g_pool.start);
+    pthread_barrier_wait(&g_pool.done);
+    return g_pool.job.parts;
+}
+
+/* first-touch + deterministic fill of every array of a CPU-PS instance, each
+ * range by its owning pool thread */
+int psx_oracle_cpu_ps_init(float *var, float *m, float *v, float *slots, size_t stride,
+                           float *const *worker_grad, float *const *worker_param, int W,
+                           size_t n, float *scratch)
+{
+    if (W < 1 || W > 64)
+        return -1;
+    cpu_ps_job j;
+    memset(&j, 0, sizeof(j));
+    j.var = var; j.m = m; j.v = v; j.slots = slots; j.scratch = scratch;
+    j.stride = stride; j.n = n; j.worker_grad = worker_grad; j.worker_param = worker_param;
+    j.W = W; j.init = 1;
+    return pool_run(&j);
+}
+
+/* One CPU-PS round on the persistent pool.  Returns the number of threads that
+ * took part (> 0) or a negative error. */
 int psx_oracle_cpu_ps_round(float *var, float *m, float *v, float *slots,
                             size_t stride, float *const *worker_grad,
                             float *const *worker_param, int W, size_t n,
@@ -276,10 +421,8 @@ int psx_oracle_cpu_ps_round(float *var, float *m, float *v, float *slots,
         return -1;
     if (W > 64)
         return -2;
-    int parts = threads > 0 ? threads : psx_oracle_threads();
-    size_t cap = n / 65536 + 1;
-    if ((size_t)parts > cap) parts = (int)cap;
-    if (parts > 256) parts = 256;
+    if (g_pool.n <= 0 && psx_oracle_pool_start(threads) <= 0)
+        return -3;
     float b1p[64], b2p[64];
     b1p[0] = opt_adam ? state[0] : 0.0f;
     b2p[0] = opt_adam ? state[1] : 0.0f;
@@ -287,20 +430,12 @@ int psx_oracle_cpu_ps_round(float *var, float *m, float *v, float *slots,
         b1p[w] = b1p[w - 1] * b1;
         b2p[w] = b2p[w - 1] * b2;
     }
-    cpu_ps_job jobs[256];
-    pthread_t tid[256];
-    for (int p = 0; p < parts; ++p) {
-        cpu_ps_job j = { var, m, v, slots, scratch, stride, n, worker_grad,
-                         worker_param, W, opt_adam, mode, p, parts,
-                         lr, b1, b2, eps, b1p, b2p };
-        jobs[p] = j;
-    }
-    for (int p = 1; p < parts; ++p)
-        if (pthread_create(&tid[p], NULL, cpu_ps_part, &jobs[p]) != 0)
-            return -3;
-    cpu_ps_part(&jobs[0]);
-    for (int p = 1; p < parts; ++p)
-        pthread_join(tid[p], NULL);
+    cpu_ps_job j = { var, m, v, slots, scratch, stride, n, worker_grad,
+                     worker_param, W, opt_adam, mode, 0, 0,
+                     lr, b1, b2, eps, b1p, b2p, 0 };
+    int parts = pool_run(&j);
+    if (parts <= 0)
+        return parts;
     int applies = (mode == PSX_ORACLE_ASYNC_ORDERED) ? W : 1;
     if (opt_adam) {
         for (int k = 0; k < applies; ++k) {

@@ -240,6 +240,12 @@ def c_lib():
                                             fl, fl, ctypes.c_int, fp, fp, i64p,
                                             ctypes.c_int]
     lib.psx_oracle_cpu_ps_round.restype = ctypes.c_int
+    lib.psx_oracle_cpu_ps_init.argtypes = [fp, fp, fp, fp, sz, fpp, fpp, ctypes.c_int, sz, fp]
+    lib.psx_oracle_cpu_ps_init.restype = ctypes.c_int
+    lib.psx_oracle_pool_start.argtypes = [ctypes.c_int]
+    lib.psx_oracle_pool_start.restype = ctypes.c_int
+    lib.psx_oracle_pool_threads.restype = ctypes.c_int
+    lib.psx_oracle_pool_stop.restype = None
     _LIB = lib
     return lib
 
@@ -295,28 +301,34 @@ class CShard:
 
 class CpuPsBaseline:
     """Multi-threaded CPU-PS round (memcpy push, apply, memcpy pull) used as the
-    timed CPU baseline by bench.py."""
+    timed CPU baseline by bench.py.  The arrays come untouched from the
+    allocator and are FIRST-TOUCHED by the pool thread that owns each range in
+    every later round (psx_oracle_cpu_ps_init), so NUMA placement is the same on
+    every run; the pool is persistent and its threads are pinned."""
 
     def __init__(self, nelem, W, opt=ADAM, lr=0.01, b1=0.9, b2=0.999, eps=1e-8,
-                 seed=7):
+                 threads=0):
         self.lib = c_lib()
         self.n, self.W, self.opt = int(nelem), int(W), opt
         self.hyper = (float(F(lr)), float(F(b1)), float(F(b2)), float(F(eps)))
-        rng = np.random.default_rng(seed)
-        self.var = rng.standard_normal(self.n, dtype=F)
-        self.m = np.zeros(self.n, F)
-        self.v = np.zeros(self.n, F)
-        self.slots = np.zeros((self.W, self.n), F)
-        self.scratch = np.zeros(self.n, F)
-        self.grads = [rng.standard_normal(self.n, dtype=F) * F(1e-2)
-                      for _ in range(self.W)]
-        self.params = [np.zeros(self.n, F) for _ in range(self.W)]
+        self.threads = self.lib.psx_oracle_pool_start(int(threads))
+        assert self.threads > 0, "thread pool failed to start (%d)" % self.threads
+        self.var = np.empty(self.n, F)           # np.empty: pages not touched yet
+        self.m = np.empty(self.n, F)
+        self.v = np.empty(self.n, F)
+        self.slots = np.empty((self.W, self.n), F)
+        self.scratch = np.empty(self.n, F)
+        self.grads = [np.empty(self.n, F) for _ in range(self.W)]
+        self.params = [np.empty(self.n, F) for _ in range(self.W)]
         self.state = np.array([b1, b2], F)
         self._step = ctypes.c_int64(0)
         fp = ctypes.POINTER(ctypes.c_float)
         self._g = (fp * self.W)(*[_fp(g) for g in self.grads])
         self._p = (fp * self.W)(*[_fp(p) for p in self.params])
-        self.threads = self.lib.psx_oracle_threads()
+        rc = self.lib.psx_oracle_cpu_ps_init(
+            _fp(self.var), _fp(self.m), _fp(self.v), _fp(self.slots), self.n, self._g,
+            self._p, self.W, self.n, _fp(self.scratch))
+        assert rc > 0, rc
 
     def round(self, mode=SUM, threads=0):
         lr, b1, b2, eps = self.hyper

@@ -33,3 +33,7 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "multigpu" in item.keywords and n < 2:
             item.add_marker(pytest.mark.skip(reason="needs >= 2 GPUs, have %d" % n))
+        elif "gpu" in item.keywords and n < 1:
+            # a plain `pytest` on a CPU-only box: the GPU tests are skipped, not failed
+            # (the product itself still has no CPU fallback -- tests/test_abi.py)
+            item.add_marker(pytest.mark.skip(reason="needs a CUDA device"))

@@ -100,11 +100,11 @@ def test_numpy_and_c_restatements_agree_bit_for_bit(opt, mode, W):
 
 def test_threaded_cpu_ps_round_equals_scalar_oracle():
     n, W = 300000, 3
-    base = o.CpuPsBaseline(n, W, o.ADAM, lr=0.01, seed=3)
+    base = o.CpuPsBaseline(n, W, o.ADAM, lr=0.01, threads=5)
     ref = o.CShard(n, o.ADAM, lr=0.01)
     ref.var[:] = base.var
     for r in range(3):
-        base.round(o.SUM, threads=5)
+        base.round(o.SUM)
         ref.round(np.stack(base.grads), o.SUM)
     assert np.array_equal(base.var, ref.var)
     assert all(np.array_equal(p, base.var) for p in base.params)

@@ -151,6 +151,9 @@ struct Shard {
     Bound bound[PSX_MAX_SLOTS];
     Mapped mailbox_map[PSX_MAX_SLOTS];
     unsigned int *mailbox[PSX_MAX_SLOTS] = {};
+    const float *mc_grad = nullptr;   // NVLS binding (psx_round_bind_mc): multicast addresses
+    float *mc_param = nullptr;        // of this shard's range in the workers' arena
+    int mc_members = 0;
     ShardHeader *hdr() const { return (ShardHeader *)base; }
     float *var() const { return (float *)(base + lay.off_var()); }
     float *m() const { return (float *)(base + lay.off_m()); }
@@ -334,6 +337,7 @@ struct ApplyRange {
     size_t off, n;
     int finish;
     unsigned int consume = 0;   // arrivals to take off the counter (counted rendez-vous)
+    int divisor = 0;            // SYNC_MEAN denominator; 0 = the slot count
 };
 
 template <int OPT, int MODE, bool SCATTER, typename SRC>
@@ -344,12 +348,13 @@ void launch_apply_t(Shard *s, SRC src, int count, const PeerSet &peers, cudaStre
     const int grid = grid_for(n4 ? n4 : 1, kApplyThreads, s->sm_count, 3);
     k_apply<OPT, MODE, SCATTER, SRC><<<grid, kApplyThreads, 0, st>>>(
         s->hdr(), (float4 *)(s->var() + r.off), (float4 *)(s->m() + r.off),
-        (float4 *)(s->v() + r.off), src, count, n4, peers, r.finish, r.consume);
+        (float4 *)(s->v() + r.off), src, count, n4, peers, r.finish, r.consume,
+        r.divisor ? r.divisor : count);
 }
 
 template <bool SCATTER, typename SRC>
 int launch_apply(Shard *s, int mode, SRC src, int count, const PeerSet &peers, cudaStream_t st,
-                 ApplyRange r = ApplyRange{0, 0, 1, 0})
+                 ApplyRange r = ApplyRange{0, 0, 1, 0, 0})
 {
     if (r.n == 0 && r.off == 0) r.n = s->lay.nelem_pad;
 #define PSX_AP(O, M) launch_apply_t<O, M, SCATTER, SRC>(s, src, count, peers, st, r)
@@ -366,6 +371,9 @@ int launch_apply(Shard *s, int mode, SRC src, int count, const PeerSet &peers, c
     return PSX_OK;
 }
 
+struct Shard;
+int launch_round_mc(Shard *s, int mode, const PeerSet &peers, cudaStream_t st, const ApplyRange &r);
+
 void fill_mirrors(Shard *s, PeerSet *p)
 {
     p->n_mirror = 0;
@@ -375,6 +383,29 @@ void fill_mirrors(Shard *s, PeerSet *p)
         if (s->mirror[c]) p->mirror[p->n_mirror++] = s->mirror[c];
         if (s->mailbox[c]) p->mailbox[p->n_mailbox++] = s->mailbox[c];
     }
+}
+
+int launch_round_mc(Shard *s, int mode, const PeerSet &peers, cudaStream_t st, const ApplyRange &r)
+{
+    const size_t n4 = r.n / 4;
+    const size_t tile = (size_t)kMcThreads * PSX_MC_UNROLL;
+    const size_t tiles = (n4 + tile - 1) / tile;
+    const size_t cap = (size_t)s->sm_count * PSX_APPLY_MIN_CTAS;
+    const int grid = (int)(tiles < 1 ? 1 : (tiles < cap ? tiles : cap));
+#define PSX_MC(O, M)                                                                          \
+    k_round_mc<O, M, PSX_MC_UNROLL><<<grid, kMcThreads, 0, st>>>(                             \
+        s->hdr(), (float4 *)(s->var() + r.off), (float4 *)(s->m() + r.off),                   \
+        (float4 *)(s->v() + r.off), s->mc_grad + r.off, s->mc_param + r.off, n4, peers,       \
+        r.consume, r.divisor)
+    const int opt = s->lay.opt;
+    if (opt == PSX_OPT_SGD && mode == PSX_MODE_SUM) PSX_MC(PSX_OPT_SGD, PSX_MODE_SUM);
+    else if (opt == PSX_OPT_SGD && mode == PSX_MODE_SYNC_MEAN) PSX_MC(PSX_OPT_SGD, PSX_MODE_SYNC_MEAN);
+    else if (opt == PSX_OPT_ADAM && mode == PSX_MODE_SUM) PSX_MC(PSX_OPT_ADAM, PSX_MODE_SUM);
+    else if (opt == PSX_OPT_ADAM && mode == PSX_MODE_SYNC_MEAN) PSX_MC(PSX_OPT_ADAM, PSX_MODE_SYNC_MEAN);
+    else return fail(PSX_EINVAL, "the NVLS round supports SUM / SYNC_MEAN (optimizer/mode %d/%d)", opt, mode);
+#undef PSX_MC
+    LAUNCH_CHECK();
+    return PSX_OK;
 }
 
 int wait_slots(Shard *s, int first, int count, uint32_t wait_seq, void *stream)
@@ -496,16 +527,21 @@ int psx_shard_destroy(uint64_t id)
         s = it->second;
         g_shards.erase(it);
     }
-    cudaSetDevice(s->device);
-    cudaDeviceSynchronize();
+    cudaError_t e = cudaSetDevice(s->device);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();   // a failed kernel surfaces here
     for (int c = 0; c < PSX_MAX_SLOTS; ++c) {
         close_mapped(s->client_map[c]);
         close_mapped(s->mailbox_map[c]);
         close_mapped(s->bound[c].grad);
         close_mapped(s->bound[c].param);
     }
-    cudaFree(s->base);
+    cudaError_t e2 = cudaFree(s->base);
     delete s;
+    if (e == cudaSuccess) e = e2;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PSX_ECUDA, "destroying shard %llu: %s", (unsigned long long)id, cudaGetErrorString(e));
+    }
     return PSX_OK;
 }
 
@@ -681,7 +717,7 @@ int psx_apply_range(uint64_t id, int mode, int first_slot, int count, uint64_t e
     PeerSet peers;
     memset(&peers, 0, sizeof(peers));
     fill_mirrors(s, &peers);
-    const ApplyRange r{(size_t)elem_off, (size_t)elem_n, finish ? 1 : 0, 0};
+    const ApplyRange r{(size_t)elem_off, (size_t)elem_n, finish ? 1 : 0, 0, 0};
     if (s->lay.wire == PSX_F32) {
         SlotSrc<float> src{(const float *)s->slot(0) + elem_off, (size_t)s->lay.nelem_pad, first_slot};
         return launch_apply<false>(s, mode, src, count, peers, (cudaStream_t)stream, r);
@@ -707,7 +743,7 @@ int psx_apply_counted(uint64_t id, int mode, int first_slot, int count, void *st
     PeerSet peers;
     memset(&peers, 0, sizeof(peers));
     fill_mirrors(s, &peers);
-    const ApplyRange r{0, (size_t)s->lay.nelem_pad, 1, (unsigned int)count};
+    const ApplyRange r{0, (size_t)s->lay.nelem_pad, 1, (unsigned int)count, 0};
     if (s->lay.wire == PSX_F32) {
         SlotSrc<float> src{(const float *)s->slot(0), (size_t)s->lay.nelem_pad, first_slot};
         return launch_apply<false>(s, mode, src, count, peers, (cudaStream_t)stream, r);
@@ -734,13 +770,39 @@ int psx_shard_register_client(uint64_t shard_id, int slot, const void *client_ha
     HandleBlob b;
     int rc = check_blob(client_handle, KIND_CLIENT, &b);
     if (rc) return rc;
-    if (s->mirror[slot]) {
-        close_mapped(s->client_map[slot]);
+    if (s->mirror[slot]) {   // re-registration (a revived worker): nothing in flight may
+        PSX_DEVICE(s->device);   // still hold the old mapping
+        CU_TRY(cudaDeviceSynchronize());
         s->mirror[slot] = nullptr;
+        close_mapped(s->client_map[slot]);
     }
     rc = open_blob(b, s->device, &s->client_map[slot]);
     if (rc) return rc;
     s->mirror[slot] = &((ClientBlock *)s->client_map[slot].base)->applied;
+    return PSX_OK;
+}
+
+/* Detach worker `slot` from the shard: drains the shard's device (no apply may be
+ * in flight that still publishes into the worker's block), then unmaps the
+ * worker's client block, mailbox and bound buffers.  The worker calls this (via
+ * its PS endpoint) BEFORE it frees those objects -- a PS that kept publishing
+ * into freed peer memory would take its own context down. */
+int psx_shard_unregister_client(uint64_t shard_id, int slot)
+{
+    Shard *s = find(g_shards, shard_id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    if (slot < 0 || slot >= PSX_MAX_SLOTS) return fail(PSX_EINVAL, "slot %d out of range", slot);
+    PSX_DEVICE(s->device);
+    CU_TRY(cudaDeviceSynchronize());
+    s->mirror[slot] = nullptr;
+    close_mapped(s->client_map[slot]);
+    s->mailbox[slot] = nullptr;
+    close_mapped(s->mailbox_map[slot]);
+    if (s->bound[slot].valid) {
+        close_mapped(s->bound[slot].grad);
+        close_mapped(s->bound[slot].param);
+        s->bound[slot].valid = false;
+    }
     return PSX_OK;
 }
 
@@ -798,11 +860,16 @@ int psx_shard_close(uint64_t id)
         c = it->second;
         g_clients.erase(it);
     }
-    cudaSetDevice(c->device);
-    cudaDeviceSynchronize();
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     close_mapped(c->shard);
-    cudaFree(c->block);
+    cudaError_t e2 = cudaFree(c->block);
     delete c;
+    if (e == cudaSuccess) e = e2;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PSX_ECUDA, "closing client %llu: %s", (unsigned long long)id, cudaGetErrorString(e));
+    }
     return PSX_OK;
 }
 
@@ -1253,14 +1320,25 @@ static int round_impl(uint64_t shard_id, int mode, int first_slot, int count, ui
     memset(&peers, 0, sizeof(peers));
     fill_mirrors(s, &peers);
     const size_t wb = s->lay.wire_bytes();
-    for (int k = 0; k < count; ++k) {
-        const Bound &b = s->bound[first_slot + k];
-        if (!b.valid) return fail(PSX_ESTATE, "slot %d has no bound buffers (psx_round_bind)", first_slot + k);
-        peers.grad[first_slot + k] = b.grad.base + b.elem_off * wb;
+    const bool nvls = s->mc_grad != nullptr;
+    if (nvls) {
+        // the switch sums ALL members' gradient copies: the round is over every worker
+        if (first_slot != 0 || count != s->mc_members)
+            return fail(PSX_EINVAL, "an NVLS round covers all %d workers (got slots [%d,%d))",
+                        s->mc_members, first_slot, first_slot + count);
+        if (mode == PSX_MODE_ASYNC_ORDERED)
+            return fail(PSX_ESTATE, "the NVLS round reduces in the switch: SUM / SYNC_MEAN only");
+        peers.mc_param = s->mc_param;
+    } else {
+        for (int k = 0; k < count; ++k) {
+            const Bound &b = s->bound[first_slot + k];
+            if (!b.valid) return fail(PSX_ESTATE, "slot %d has no bound buffers (psx_round_bind)", first_slot + k);
+            peers.grad[first_slot + k] = b.grad.base + b.elem_off * wb;
+        }
+        for (int c = 0; c < PSX_MAX_SLOTS; ++c)  // every bound worker receives the new parameters
+            if (s->bound[c].valid)
+                peers.param[peers.n_param++] = s->bound[c].param.base + s->bound[c].elem_off * wb;
     }
-    for (int c = 0; c < PSX_MAX_SLOTS; ++c)  // every bound worker receives the new parameters
-        if (s->bound[c].valid)
-            peers.param[peers.n_param++] = s->bound[c].param.base + s->bound[c].elem_off * wb;
     PSX_DEVICE(s->device);
     if (counted) {
         rc = stream_wait_geq(stream, &s->hdr()->arrivals, (uint32_t)count);
@@ -1270,7 +1348,8 @@ static int round_impl(uint64_t shard_id, int mode, int first_slot, int count, ui
         rc = wait_slots(s, first_slot, count, wait_seq, stream);
     }
     if (rc) return rc;
-    const ApplyRange r{0, (size_t)s->lay.nelem_pad, 1, counted ? (unsigned int)count : 0u};
+    const ApplyRange r{0, (size_t)s->lay.nelem_pad, 1, counted ? (unsigned int)count : 0u, count};
+    if (nvls) return launch_round_mc(s, mode, peers, (cudaStream_t)stream, r);
     if (s->lay.wire == PSX_F32) {
         PeerSrc<float> src{peers, first_slot};
         return launch_apply<true>(s, mode, src, count, peers, (cudaStream_t)stream, r);

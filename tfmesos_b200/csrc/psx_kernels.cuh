@@ -51,6 +51,8 @@ struct PeerSet {                      // by-value kernel argument (PS address sp
     void *param[PSX_MAX_SLOTS];       // bound worker parameter buffers, compact, wire dtype
     unsigned int *mirror[PSX_MAX_SLOTS];  // ClientBlock::applied of each client, compact
     unsigned int *mailbox[PSX_MAX_SLOTS]; // per-worker completion counters, compact
+    float *mc_param;                      // NVLS: multicast address of every worker's parameter
+                                          // buffer (one multimem.st reaches all of them)
     int n_param;
     int n_mirror;
     int n_mailbox;
@@ -140,12 +142,17 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(flo
 // system-scope fence and stores the flag(s).  (A MEMBAR.SYS costs ~3 us;
 // paying it once per kernel instead of once per CTA is what keeps 300 KB
 // MNIST-sized rounds in the 10 us range -- profiles/r01.)
+template <bool SYS_FENCE = false>
 __device__ __forceinline__ bool last_cta(unsigned int *ticket)
 {
     __shared__ bool s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
+        // SYS_FENCE: the CTA's own writes went through the NVSwitch multicast path
+        // (multimem.st); order them at system scope here instead of relying on the
+        // last CTA's fence to cover other SMs' in-switch replications
+        if (SYS_FENCE) __threadfence_system();
+        else __threadfence();
         unsigned int t = atomicAdd(ticket, 1u);
         s_last = (t == gridDim.x - 1);
     }
@@ -285,34 +292,43 @@ k_list_tma(const ListChunk *__restrict__ chunks, int n_chunks, char *shard_base,
     auto chunk_of = [&](int j) { return chunks[(size_t)blockIdx.x + (size_t)j * gridDim.x]; };
 
     if (threadIdx.x == 0) {
-        constexpr int D = kListStages - 2;            // loads kept in flight
-        auto issue_load = [&](int j) {
-            const ListChunk c = chunk_of(j);
-            if (c.plain) return;
-            const int s = j % kListStages;
-            const char *src = to_shard ? c.tensor : shard_base + c.shard_off;
-            mbar_expect_tx(&full[s], c.bytes);
-            tma_load_1d(ring + (size_t)s * kListChunkBytes, src, c.bytes, &full[s]);
+        // Ring stage and mbarrier phase are taken from a RUNNING COUNT of the TMA
+        // chunks this CTA has issued / consumed, never from the chunk index j:
+        // plain chunks (ragged tails, unaligned tensors) sit in between the TMA
+        // chunks of a list and issue no load, so indexing by j would leave a
+        // stage's barrier one phase behind (stale data or a hang once a CTA owns
+        // more than kListStages chunks).
+        constexpr int D = kListStages - 2;            // TMA loads kept in flight
+        int next_issue = 0;                           // next chunk index to look at for a load
+        int issued = 0, consumed = 0;                 // TMA chunks so far
+        auto issue_one = [&]() {                      // issue the next TMA chunk, if any
+            while (next_issue < mine) {
+                const ListChunk c = chunk_of(next_issue++);
+                if (c.plain) continue;
+                const int s = issued % kListStages;
+                const char *src = to_shard ? c.tensor : shard_base + c.shard_off;
+                mbar_expect_tx(&full[s], c.bytes);
+                tma_load_1d(ring + (size_t)s * kListChunkBytes, src, c.bytes, &full[s]);
+                ++issued;
+                return;
+            }
         };
-        for (int j = 0; j < D && j < mine; ++j) issue_load(j);
+        for (int k = 0; k < D; ++k) issue_one();
         for (int j = 0; j < mine; ++j) {
-            if (j + D < mine) {
-                // stage (j+D)%S was last read by chunk j-2's store; one bulk group is
-                // committed per iteration, so "all but the newest" covers it
-                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                issue_load(j + D);
-            }
             const ListChunk c = chunk_of(j);
-            if (c.plain) {
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // keep the count
-                continue;
-            }
-            const int s = j % kListStages;
-            mbar_wait(&full[s], (uint32_t)((j / kListStages) & 1));
+            if (c.plain) continue;
+            // stage (consumed+D)%S was last read by the store of TMA chunk
+            // consumed-2; one bulk group is committed per consumed chunk, so "all
+            // but the newest" covers it
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            issue_one();
+            const int s = consumed % kListStages;
+            mbar_wait(&full[s], (uint32_t)((consumed / kListStages) & 1));
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             char *dst = to_shard ? shard_base + c.shard_off : c.tensor;
             tma_store_1d(dst, ring + (size_t)s * kListChunkBytes, c.bytes);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            ++consumed;
         }
         asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores performed
         asm volatile("fence.proxy.async;" ::: "memory");
@@ -444,6 +460,38 @@ __device__ __forceinline__ float4 div4(const float4 &a, float d)
     return make_float4(__fdiv_rn(a.x, d), __fdiv_rn(a.y, d), __fdiv_rn(a.z, d), __fdiv_rn(a.w, d));
 }
 
+// Epilogue of every apply / round kernel: the CTA that draws the last ticket
+// advances the beta powers and global_step (AdamOptimizer._finish, once per
+// apply) and publishes completion to every registered worker.
+// finish == 0: a partial (element-range) apply that is not the last of its
+// round -- it must not advance the beta powers / global_step / apply_seq.
+template <int OPT, bool SYS_FENCE>
+__device__ __forceinline__ void finish_apply(ShardHeader *h, const PeerSet &peers, int applies,
+                                             int finish, float b1, float b2)
+{
+    const bool last = last_cta<SYS_FENCE>(&h->ticket);
+    if (last && threadIdx.x == 0 && !finish) {
+        h->ticket = 0;
+    } else if (last && threadIdx.x == 0) {
+        if (OPT == PSX_OPT_ADAM) {
+            float p1 = h->b1p, p2 = h->b2p;
+            for (int k = 0; k < applies; ++k) {
+                p1 = __fmul_rn(p1, b1);
+                p2 = __fmul_rn(p2, b2);
+            }
+            h->b1p = p1;
+            h->b2p = p2;
+        }
+        h->step += applies;
+        h->ticket = 0;
+        const unsigned int seq = h->apply_seq + 1;
+        __threadfence_system();
+        publish_store(&h->apply_seq, seq);
+        for (int c = 0; c < peers.n_mirror; ++c) publish_store(peers.mirror[c], seq);
+        for (int c = 0; c < peers.n_mailbox; ++c) publish_add(peers.mailbox[c], 1u);
+    }
+}
+
 constexpr int kApplyThreads = 256;
 constexpr int kSlotChunk = 4;  // gradient vectors in flight per thread
 #ifndef PSX_APPLY_MIN_CTAS
@@ -474,8 +522,30 @@ template <typename WIRE> struct PeerSrc {            // bound worker buffers (pe
         return Vec4<WIRE>::load((const WIRE *)peers.grad[first + s] + 4 * i);
     }
 };
+// NVLS: ONE multicast address stands for the same range of EVERY worker's gradient
+// buffer; multimem.ld_reduce makes the switch fetch all copies and return their
+// f32 sum, so the kernel sees a single "slot" (count == 1) that already holds the
+// W-way reduction.  The switch's summation order is its own: bit-exact against
+// the oracle's slot order only for W <= 2 (a single commutative add), tolerance-
+// checked beyond.
+__device__ __forceinline__ float4 mc_ld_reduce(const float *mc)
+{
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(mc)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void mc_st(float *mc, const float4 &v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x),
+                 "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
 template <typename SRC> struct WireOf { using type = float; };
 template <typename W> struct WireOf<PeerSrc<W>> { using type = W; };
+template <typename SRC> struct IsMulticast { static constexpr bool value = false; };
 
 // Fused reduce + apply over a whole shard (n4 vectors).  SCATTER: also write
 // the new parameters into every bound worker parameter buffer (psx_round).
@@ -483,8 +553,11 @@ template <int OPT, int MODE, bool SCATTER, typename SRC>
 __global__ void __launch_bounds__(kApplyThreads, PSX_APPLY_MIN_CTAS)
 k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restrict__ mom,
         float4 *__restrict__ vel, SRC src, int count, size_t n4, PeerSet peers, int finish,
-        unsigned int consume)
+        unsigned int consume, int divisor)
 {
+    // count   = gradient sources read per element (1 on the NVLS path: the switch
+    //           has already summed the workers' copies)
+    // divisor = SYNC_MEAN's denominator (the number of workers aggregated)
     // counted rendez-vous: the stream waited for arrivals >= consume right before
     // this launch; take them off the counter so the next round waits for the same
     // constant again (that is what makes a round replayable from a CUDA graph).
@@ -507,7 +580,7 @@ k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restric
         }
         __syncthreads();
     }
-    const float fcount = (float)count;
+    const float fcount = (float)divisor;
 
     // Software pipeline: the first kSlotChunk gradient vectors of the NEXT
     // iteration are requested before this iteration's arithmetic.  With peer
@@ -601,30 +674,96 @@ k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restric
         }
     }
 
-    // finish == 0: a partial (element-range) apply that is not the last of its
-    // round -- it must not advance the beta powers / global_step / apply_seq
-    const bool last = last_cta(&h->ticket);
-    if (last && threadIdx.x == 0 && !finish) {
-        h->ticket = 0;
-    } else if (last && threadIdx.x == 0) {
-        const int applies = (MODE == PSX_MODE_ASYNC_ORDERED) ? count : 1;
-        if (OPT == PSX_OPT_ADAM) {
-            float p1 = h->b1p, p2 = h->b2p;
-            for (int k = 0; k < applies; ++k) {
-                p1 = __fmul_rn(p1, b1);
-                p2 = __fmul_rn(p2, b2);
-            }
-            h->b1p = p1;
-            h->b2p = p2;
+    finish_apply<OPT, IsMulticast<SRC>::value>(h, peers, (MODE == PSX_MODE_ASYNC_ORDERED) ? count : 1,
+                                                finish, b1, b2);
+}
+
+// ------------------------------------------------------------- NVLS round ----
+// The one-kernel PS round with the NVSwitch doing both collective legs
+// (psx_round on a shard bound with psx_round_bind_mc).  Per 16-byte vector of the
+// shard's stripe:
+//     g  = multimem.ld_reduce.add.v4.f32 [grad_mc + i]   switch fetches the vector from
+//                                                        EVERY worker's gradient buffer
+//                                                        and returns the f32 sum
+//     SGD / Adam on var, m, v in local HBM
+//     multimem.st.v4.f32 [param_mc + i], var'            switch replicates the store into
+//                                                        EVERY worker's parameter buffer
+// NVLink bytes per GPU and direction for a bucket of B bytes striped over N GPUs:
+// B (gradient copies leaving for the switch) + B/N (parameter stripe leaving) out,
+// B/N (reduced stripe) + B (all stripes' parameters) in -- B(1 + 1/N) against the
+// unicast kernel's 2(N-1)/N B.  The gather saturates the port's egress and the
+// scatter its ingress, so they must overlap: each thread keeps the ld_reduce of
+// its NEXT tile in flight while it applies and multicasts the current one.
+constexpr int kMcThreads = 256;
+#ifndef PSX_MC_UNROLL
+#define PSX_MC_UNROLL 2            // vectors per thread and tile (ld_reduce in flight: 2x this)
+#endif
+
+template <int OPT, int MODE, int U>
+__global__ void __launch_bounds__(kMcThreads, PSX_APPLY_MIN_CTAS)
+k_round_mc(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restrict__ mom,
+           float4 *__restrict__ vel, const float *grad_mc, float *param_mc, size_t n4,
+           PeerSet peers, unsigned int consume, int divisor)
+{
+    if (consume != 0 && blockIdx.x == 0 && threadIdx.x == 0) atomicSub(&h->arrivals, consume);
+    const float lr = h->lr, b1 = h->b1, b2 = h->b2, eps = h->eps;
+    const float omb1 = __fsub_rn(1.0f, b1);
+    const float omb2 = __fsub_rn(1.0f, b2);
+    const float alpha = (OPT == PSX_OPT_ADAM) ? adam_alpha(lr, h->b1p, h->b2p) : 0.f;
+    const float fdiv = (float)divisor;
+
+    const size_t tile = (size_t)kMcThreads * U;
+    const size_t tiles = (n4 + tile - 1) / tile;
+    size_t t = blockIdx.x;
+    float4 gn[U];
+    if (t < tiles) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = t * tile + (size_t)u * kMcThreads + threadIdx.x;
+            if (i < n4) gn[u] = mc_ld_reduce(grad_mc + 4 * i);
         }
-        h->step += applies;
-        h->ticket = 0;
-        const unsigned int seq = h->apply_seq + 1;
-        __threadfence_system();
-        publish_store(&h->apply_seq, seq);
-        for (int c = 0; c < peers.n_mirror; ++c) publish_store(peers.mirror[c], seq);
-        for (int c = 0; c < peers.n_mailbox; ++c) publish_add(peers.mailbox[c], 1u);
     }
+    for (; t < tiles; t += gridDim.x) {
+        float4 g[U], x[U], m[U], v[U];
+        const size_t base = t * tile + threadIdx.x;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {          // local state first: HBM latency overlaps the switch's
+            const size_t i = base + (size_t)u * kMcThreads;
+            if (i < n4) {
+                x[u] = ld_stream(var + i);
+                if (OPT == PSX_OPT_ADAM) {
+                    m[u] = ld_stream(mom + i);
+                    v[u] = ld_stream(vel + i);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) g[u] = gn[u];
+        const size_t tn = t + gridDim.x;
+        if (tn < tiles) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t i = tn * tile + (size_t)u * kMcThreads + threadIdx.x;
+                if (i < n4) gn[u] = mc_ld_reduce(grad_mc + 4 * i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t i = base + (size_t)u * kMcThreads;
+            if (i < n4) {
+                float4 acc = g[u];
+                if (MODE == PSX_MODE_SYNC_MEAN) acc = div4(acc, fdiv);
+                apply4<OPT>(x[u], m[u], v[u], acc, lr, alpha, omb1, omb2, eps);
+                st_stream(var + i, x[u]);
+                if (OPT == PSX_OPT_ADAM) {
+                    st_stream(mom + i, m[u]);
+                    st_stream(vel + i, v[u]);
+                }
+                mc_st(param_mc + 4 * i, x[u]);
+            }
+        }
+    }
+    finish_apply<OPT, true>(h, peers, 1, 1, b1, b2);
 }
 
 }  // namespace psx

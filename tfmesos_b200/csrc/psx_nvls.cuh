@@ -1,8 +1,13 @@
-// psx_nvls.cuh -- NVSwitch multicast (NVLS) primitives, single-process form.
-// Included at the end of psx.cu.  EXPERIMENTAL: measured on 2 GPUs only
-// (profiles/); not used by psx_round (DESIGN.md section 6 explains why the
-// striped PS round gains from NVLS only from N = 4 GPUs and only as a
-// tolerance-checked mode).
+// psx_nvls.cuh -- NVSwitch multicast (NVLS) objects.  Included at the end of psx.cu.
+//
+// Two forms:
+//   psx_mc_*   all member GPUs in ONE process (micro-benchmarks, tests/test_gpu_nvls.py)
+//   psx_mcx_*  one MEMBER per (process, GPU): the multicast object's POSIX file
+//              descriptor travels from the creating process to the others over an
+//              AF_UNIX socket (SCM_RIGHTS; the Python host does that), every
+//              member adds its device, then binds its own VMM allocation.  This
+//              is what the NVLS form of psx_round uses (psx_round_bind_mc): the
+//              product runs one process per GPU.
 //
 //   multicast buffer = one cuMemCreate allocation per GPU, all bound at offset 0
 //   of ONE multicast object (cuMulticastCreate / AddDevice / BindMem), mapped
@@ -34,6 +39,8 @@ struct DriverVmm {
     CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
     CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+    CUresult (*MemExportToShareableHandle)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType) = nullptr;
     bool ok = false;
 };
 DriverVmm g_drv;
@@ -69,6 +76,8 @@ int load_driver_vmm()
         ok &= drv_resolve("cuMemUnmap", &g_drv.MemUnmap);
         ok &= drv_resolve("cuMemSetAccess", &g_drv.MemSetAccess);
         ok &= drv_resolve("cuGetErrorString", &g_drv.GetErrorString);
+        ok &= drv_resolve("cuMemExportToShareableHandle", &g_drv.MemExportToShareableHandle);
+        ok &= drv_resolve("cuMemImportFromShareableHandle", &g_drv.MemImportFromShareableHandle);
         g_drv.ok = ok;
     });
     if (!g_drv.ok) return fail(PSX_ECUDA, "the driver does not expose the VMM / multicast entry points");
@@ -309,6 +318,227 @@ int psx_mc_reduce(uint64_t id, int member, void *dst_dev, uint64_t off_bytes, ui
     const int grid = grid_for(n4 ? n4 : 1, 256, sm_count_of(b->device[member]), 8);
     k_mc_reduce<<<grid, 256, 0, (cudaStream_t)stream>>>((float4 *)dst_dev, (const float *)(b->mcva + off_bytes), n4);
     LAUNCH_CHECK();
+    return PSX_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------- multi-process members ----
+namespace {
+
+struct McMember {
+    int device = 0;
+    int n_devices = 0;
+    size_t size = 0, gran = 0;
+    CUmemGenericAllocationHandle mc = 0, mem = 0;
+    CUdeviceptr uc = 0, mcva = 0;
+    bool added = false, bound = false;
+    int fd = -1;                  // creator only: the exported descriptor (owned here)
+};
+std::unordered_map<uint64_t, McMember *> g_mcx;
+
+int mcx_prop(int n_devices, uint64_t nbytes, CUmulticastObjectProp *prop, size_t *gran)
+{
+    memset(prop, 0, sizeof(*prop));
+    prop->numDevices = (unsigned)n_devices;
+    prop->size = nbytes;
+    prop->handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    DRV_TRY(g_drv.MulticastGetGranularity(gran, prop, CU_MULTICAST_GRANULARITY_RECOMMENDED),
+            "cuMulticastGetGranularity");
+    prop->size = (nbytes + *gran - 1) / *gran * *gran;
+    return PSX_OK;
+}
+
+void mcx_release(McMember *m)
+{
+    if (m->uc) {
+        g_drv.MemUnmap(m->uc, m->size);
+        g_drv.MemAddressFree(m->uc, m->size);
+    }
+    if (m->mcva) {
+        g_drv.MemUnmap(m->mcva, m->size);
+        g_drv.MemAddressFree(m->mcva, m->size);
+    }
+    if (m->bound) {
+        CUdevice d;
+        if (g_drv.DeviceGet(&d, m->device) == CUDA_SUCCESS) g_drv.MulticastUnbind(m->mc, d, 0, m->size);
+    }
+    if (m->mem) g_drv.MemRelease(m->mem);
+    if (m->mc) g_drv.MemRelease(m->mc);
+    if (m->fd >= 0) close(m->fd);
+    delete m;
+}
+
+int mcx_common(int device, int n_devices, uint64_t nbytes, McMember **out, CUmulticastObjectProp *prop)
+{
+    if (n_devices < 1 || n_devices > kMcMaxDevices || nbytes == 0)
+        return fail(PSX_EINVAL, "multicast member: 1..%d devices and a non-empty size", kMcMaxDevices);
+    int rc = load_driver_vmm();
+    if (rc) return rc;
+    PSX_DEVICE(device);
+    CU_TRY(cudaFree(0));
+    int sup = 0;
+    rc = psx_nvls_supported(device, &sup);
+    if (rc) return rc;
+    if (!sup) return fail(PSX_ECUDA, "device %d does not support NVSwitch multicast", device);
+    size_t gran = 0;
+    rc = mcx_prop(n_devices, nbytes, prop, &gran);
+    if (rc) return rc;
+    McMember *m = new McMember();
+    m->device = device;
+    m->n_devices = n_devices;
+    m->size = prop->size;
+    m->gran = gran;
+    *out = m;
+    return PSX_OK;
+}
+
+uint64_t mcx_register(McMember *m)
+{
+    uint64_t id = g_next_id.fetch_add(1);
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_mcx[id] = m;
+    return id;
+}
+
+}  // namespace
+
+extern "C" {
+
+int psx_mcx_create(int device, int n_devices, uint64_t nbytes, int *out_fd, uint64_t *out_id)
+{
+    if (!out_fd || !out_id) return fail(PSX_EINVAL, "null out pointer");
+    McMember *m = nullptr;
+    CUmulticastObjectProp prop;
+    int rc = mcx_common(device, n_devices, nbytes, &m, &prop);
+    if (rc) return rc;
+    CUresult r = g_drv.MulticastCreate(&m->mc, &prop);
+    if (r != CUDA_SUCCESS) {
+        mcx_release(m);
+        return drv_fail("cuMulticastCreate", r);
+    }
+    int fd = -1;
+    r = g_drv.MemExportToShareableHandle(&fd, m->mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+    if (r != CUDA_SUCCESS) {
+        mcx_release(m);
+        return drv_fail("cuMemExportToShareableHandle(multicast)", r);
+    }
+    m->fd = fd;
+    *out_fd = fd;
+    *out_id = mcx_register(m);
+    return PSX_OK;
+}
+
+int psx_mcx_import(int device, int n_devices, uint64_t nbytes, int fd, uint64_t *out_id)
+{
+    if (!out_id || fd < 0) return fail(PSX_EINVAL, "bad descriptor / null out id");
+    McMember *m = nullptr;
+    CUmulticastObjectProp prop;
+    int rc = mcx_common(device, n_devices, nbytes, &m, &prop);
+    if (rc) return rc;
+    CUresult r = g_drv.MemImportFromShareableHandle(&m->mc, (void *)(uintptr_t)fd,
+                                                    CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+    if (r != CUDA_SUCCESS) {
+        mcx_release(m);
+        return drv_fail("cuMemImportFromShareableHandle(multicast)", r);
+    }
+    *out_id = mcx_register(m);
+    return PSX_OK;
+}
+
+int psx_mcx_add_device(uint64_t id)
+{
+    McMember *m = find(g_mcx, id);
+    if (!m) return fail(PSX_EINVAL, "unknown multicast member id");
+    if (m->added) return PSX_OK;
+    CUdevice d;
+    DRV_TRY(g_drv.DeviceGet(&d, m->device), "cuDeviceGet");
+    DRV_TRY(g_drv.MulticastAddDevice(m->mc, d), "cuMulticastAddDevice");
+    m->added = true;
+    return PSX_OK;
+}
+
+/* Call after EVERY member has added its device (host barrier in between):
+ * cuMulticastBindMem needs the complete team. */
+int psx_mcx_bind(uint64_t id, void **out_unicast, void **out_multicast, uint64_t *out_size)
+{
+    McMember *m = find(g_mcx, id);
+    if (!m) return fail(PSX_EINVAL, "unknown multicast member id");
+    if (!m->added) return fail(PSX_ESTATE, "psx_mcx_add_device first");
+    if (!m->bound) {
+        PSX_DEVICE(m->device);
+        CUmemAllocationProp ap;
+        memset(&ap, 0, sizeof(ap));
+        ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        ap.location.id = m->device;
+        ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+        DRV_TRY(g_drv.MemCreate(&m->mem, m->size, &ap, 0), "cuMemCreate");
+        DRV_TRY(g_drv.MulticastBindMem(m->mc, 0, m->mem, 0, m->size, 0), "cuMulticastBindMem");
+        m->bound = true;
+        CUmemAccessDesc access;
+        access.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        access.location.id = m->device;
+        access.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        DRV_TRY(g_drv.MemAddressReserve(&m->uc, m->size, m->gran, 0, 0), "cuMemAddressReserve(unicast)");
+        DRV_TRY(g_drv.MemMap(m->uc, m->size, 0, m->mem, 0), "cuMemMap(unicast)");
+        DRV_TRY(g_drv.MemSetAccess(m->uc, m->size, &access, 1), "cuMemSetAccess(unicast)");
+        DRV_TRY(g_drv.MemAddressReserve(&m->mcva, m->size, m->gran, 0, 0), "cuMemAddressReserve(multicast)");
+        DRV_TRY(g_drv.MemMap(m->mcva, m->size, 0, m->mc, 0), "cuMemMap(multicast)");
+        DRV_TRY(g_drv.MemSetAccess(m->mcva, m->size, &access, 1), "cuMemSetAccess(multicast)");
+        CU_TRY(cudaMemset((void *)m->uc, 0, m->size));
+        CU_TRY(cudaDeviceSynchronize());
+    }
+    if (out_unicast) *out_unicast = (void *)m->uc;
+    if (out_multicast) *out_multicast = (void *)m->mcva;
+    if (out_size) *out_size = m->size;
+    return PSX_OK;
+}
+
+int psx_mcx_destroy(uint64_t id)
+{
+    McMember *m = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_mcx.find(id);
+        if (it == g_mcx.end()) return fail(PSX_EINVAL, "unknown multicast member id");
+        m = it->second;
+        g_mcx.erase(it);
+    }
+    cudaSetDevice(m->device);
+    cudaError_t e = cudaDeviceSynchronize();
+    mcx_release(m);
+    if (e != cudaSuccess) return fail(PSX_ECUDA, "draining the device before unbinding: %s", cudaGetErrorString(e));
+    return PSX_OK;
+}
+
+/* The NVLS form of psx_round_bind: instead of W unicast peer mappings, the shard
+ * gets the multicast addresses of its range inside the workers' arena --
+ * grad_off_bytes / param_off_bytes locate the bucket's gradient and parameter
+ * tensors in the arena (identical in every member), elem_off the shard's first
+ * element inside the bucket.  psx_round / psx_round_counted then gather with
+ * multimem.ld_reduce and scatter with multimem.st.  The shard's device must be a
+ * member (it issues the multimem operations through its own mapping). */
+int psx_round_bind_mc(uint64_t shard_id, uint64_t mcx_id, uint64_t grad_off_bytes,
+                      uint64_t param_off_bytes, uint64_t elem_off, int n_members)
+{
+    Shard *s = find(g_shards, shard_id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    McMember *m = find(g_mcx, mcx_id);
+    if (!m) return fail(PSX_EINVAL, "unknown multicast member id");
+    if (!m->bound) return fail(PSX_ESTATE, "psx_mcx_bind first");
+    if (m->device != s->device) return fail(PSX_EINVAL, "the multicast member must live on the shard's device");
+    if (s->lay.wire != PSX_F32) return fail(PSX_ESTATE, "the NVLS round needs an f32 wire format");
+    if (elem_off % 4 || grad_off_bytes % 16 || param_off_bytes % 16)
+        return fail(PSX_EINVAL, "offsets must be 16-byte granular");
+    if (n_members < 1 || n_members > m->n_devices) return fail(PSX_EINVAL, "n_members %d outside 1..%d", n_members, m->n_devices);
+    const uint64_t span = (elem_off + s->lay.nelem_pad) * 4;
+    if (grad_off_bytes + span > m->size || param_off_bytes + span > m->size)
+        return fail(PSX_EINVAL, "shard range [%llu,+%llu) elements does not fit the %zu-byte arena",
+                    (unsigned long long)elem_off, (unsigned long long)s->lay.nelem_pad, m->size);
+    s->mc_grad = (const float *)(m->mcva + grad_off_bytes) + elem_off;
+    s->mc_param = (float *)(m->mcva + param_off_bytes) + elem_off;
+    s->mc_members = n_members;
     return PSX_OK;
 }
 

@@ -15,6 +15,7 @@ PS task live in ONE flat f32 bucket in that GPU's HBM (one kernel per round,
 not one RPC per variable), and a bucket may additionally be striped over
 several GPUs to spread the NVLink ingress.
 """
+import os
 from collections import OrderedDict
 
 from . import psx
@@ -149,10 +150,14 @@ class Topology(object):
 class ParameterServer(object):
     """One shard of one PS task, resident on one GPU."""
 
-    def __init__(self, spec, optimizer, n_workers, wire=psx.F32, landing_slots=True):
+    def __init__(self, spec, optimizer, n_workers, wire=psx.F32, landing_slots=True,
+                 device=None):
+        """device: physical CUDA ordinal when it differs from the topology's logical
+        one (several ranks sharing a GPU; CUDA_VISIBLE_DEVICES remapping)."""
         self.spec = spec
         self.n_workers = int(n_workers)
-        self.shard = psx.Shard(spec.device, spec.nelem, optimizer.opt,
+        self.device = spec.device if device is None else int(device)
+        self.shard = psx.Shard(self.device, spec.nelem, optimizer.opt,
                                optimizer.learning_rate, optimizer.beta1, optimizer.beta2,
                                optimizer.epsilon,
                                n_slots=self.n_workers if landing_slots else 0, wire=wire)
@@ -177,25 +182,37 @@ class Worker(object):
     flat parameter tensor per PS task in ITS OWN HBM (what TF keeps as the
     worker-side copies it _Recv'd / will _Send), with per-variable views."""
 
-    def __init__(self, index, topology, handles, exportable=False, wire=psx.F32):
+    def __init__(self, index, topology, handles, exportable=False, wire=psx.F32, device=None,
+                 arena=None):
         """handles: {(task, stripe): shard handle bytes}.  wire: element type of
         this worker's gradient / parameter tensors (f32, or bf16 for BASELINE
-        config #4 -- the PS keeps f32 master copies either way)."""
+        config #4 -- the PS keeps f32 master copies either way).  device: physical
+        CUDA ordinal if it differs from the topology's logical one.  arena: an
+        object with ``carve(nbytes) -> (ptr, tensor_factory)`` that provides the
+        staging memory instead of psx.Buffer (the NVLS multicast arena)."""
         import torch
         self.index = int(index)
         self.wire = wire
         dtype = torch.bfloat16 if wire == psx.BF16 else torch.float32
         esize = 2 if wire == psx.BF16 else 4
         self.topo = topology
-        self.device = topology.worker_devices[self.index]
+        self.logical_device = topology.worker_devices[self.index]
+        self.device = self.logical_device if device is None else int(device)
         self.layout = topology.layout
         dev = torch.device("cuda", self.device)
         self.buffers = []
+        self.arena_offsets = []         # per task: (grad byte offset, param byte offset)
         self.grad_flat, self.param_flat = [], []
         for task in range(self.layout.ps_tasks):
             shards = topology.shards_of(task)
             n = _round_up(sum(s.nelem for s in shards), STRIPE_ALIGN)
-            if exportable:      # psx_round needs IPC-exportable staging
+            if arena is not None:
+                goff, g = arena.carve(n * esize, dtype)
+                poff, p = arena.carve(n * esize, dtype)
+                self.arena_offsets.append((goff, poff))
+                self.grad_flat.append(g)
+                self.param_flat.append(p)
+            elif exportable:    # psx_round needs IPC-exportable staging
                 g, p = psx.Buffer(self.device, n * esize), psx.Buffer(self.device, n * esize)
                 self.buffers.append((g, p))
                 self.grad_flat.append(g.tensor(dtype))
@@ -212,7 +229,8 @@ class Worker(object):
         # (incast: measured 8 ms vs ~3 ms per staged round at N=8, profiles/r08).
         ngpu = max([s.device for s in topology.shards] + list(topology.worker_devices)) + 1
         self.order = sorted(topology.shards,
-                            key=lambda s: ((s.device - self.device) % ngpu, s.task, s.stripe))
+                            key=lambda s: ((s.device - self.logical_device) % ngpu, s.task,
+                                           s.stripe))
         self.params, self.grads = OrderedDict(), OrderedDict()
         for name, (task, off, shape, numel) in self.layout.entries.items():
             self.params[name] = self.param_flat[task][off:off + numel].view(shape)
@@ -378,58 +396,180 @@ def merge_across_ranks(mine):
     return merged
 
 
-def torchrun_topology(layout, world, stripes=None):
-    """Stripe j of PS task t is pinned to GPU (t + j) mod world; worker r runs on
-    GPU r.  Same arguments -> same topology on every rank."""
-    stripes = world if stripes is None else max(1, int(stripes))
-    ps_devices = [[(t + j) % world for j in range(stripes)] for t in range(layout.ps_tasks)]
-    return Topology(layout, ps_devices, list(range(world)))
+def torchrun_topology(layout, world, stripes=None, ps_ranks=None, worker_ranks=None):
+    """Default: stripe j of PS task t is pinned to GPU (t + j) mod world and worker r
+    runs on GPU r.  ``ps_ranks`` (one rank or list of ranks per PS task) and
+    ``worker_ranks`` place them explicitly -- e.g. BASELINE config #3 as written,
+    2 ps + 4 workers: ps_ranks=[0, 1], worker_ranks=[2, 3, 4, 5] (the first-fit
+    order of tfmesos/scheduler.py:252-275: ps tasks first, then workers).
+    Same arguments -> same topology on every rank."""
+    if ps_ranks is None:
+        stripes = world if stripes is None else max(1, int(stripes))
+        ps_ranks = [[(t + j) % world for j in range(stripes)] for t in range(layout.ps_tasks)]
+    else:
+        ps_ranks = [[r] if isinstance(r, int) else list(r) for r in ps_ranks]
+        if stripes is not None and len(ps_ranks) == layout.ps_tasks:
+            # more stripes than listed ranks: cycle over them (pipelining granularity)
+            ps_ranks = [[rs[j % len(rs)] for j in range(max(len(rs), int(stripes)))]
+                        for rs in ps_ranks]
+        assert len(ps_ranks) == layout.ps_tasks, "one rank (list) per PS task"
+    if worker_ranks is None:
+        worker_ranks = list(range(world))
+    return Topology(layout, ps_ranks, list(worker_ranks))
+
+
+class McArena(object):
+    """This rank's member of one NVSwitch multicast object shared by all worker
+    ranks (psx_mcx_*): a VMM allocation in this GPU's HBM that is mapped twice --
+    at a unicast address (ordinary loads / stores: the torch views below) and,
+    together with every other member's allocation, at ONE multicast address on
+    which the switch executes multimem.ld_reduce (sum over all members) and
+    multimem.st (store to all members).  The multicast object's POSIX fd goes from
+    rank 0 to the other processes over an AF_UNIX socket (SCM_RIGHTS); CUDA-IPC
+    blobs cannot carry it."""
+
+    def __init__(self, device, nbytes, rank, world, broadcast):
+        """broadcast(obj_or_None) -> obj: rank 0's object on every rank."""
+        import socket
+        self.device, self.rank, self.world = int(device), int(rank), int(world)
+        self.cursor = 0
+        fd = -1
+        if rank == 0:
+            self.mcx = psx.McMember.create(device, world, nbytes)
+            fd = self.mcx.fd
+        if world > 1:
+            if rank == 0:
+                name = "\0psx-mc-%d-%d" % (os.getpid(), id(self) & 0xFFFFFF)
+                srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                srv.bind(name)
+                srv.listen(world)
+                broadcast(name)
+                for _ in range(world - 1):
+                    conn, _ = srv.accept()
+                    socket.send_fds(conn, [b"mc"], [fd])
+                    conn.recv(1)            # the peer has imported: its copy of the fd is live
+                    conn.close()
+                srv.close()
+            else:
+                name = broadcast(None)
+                c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                c.connect(name)
+                _, fds, _, _ = socket.recv_fds(c, 16, 1)
+                self.mcx = psx.McMember.import_fd(device, world, nbytes, fds[0])
+                os.close(fds[0])
+                c.send(b"k")
+                c.close()
+        self.mcx.add_device()
+
+    def bind(self):
+        """After EVERY member has added its device (barrier in between)."""
+        self.uc, self.mc, self.size = self.mcx.bind()
+
+    def carve(self, nbytes, dtype):
+        import torch
+        nbytes = _round_up(int(nbytes), 4096)
+        off = self.cursor
+        assert off + nbytes <= self.size, "multicast arena exhausted"
+        self.cursor += nbytes
+        esz = torch.empty(0, dtype=dtype).element_size()
+        return off, psx.device_tensor(self.uc + off, nbytes // esz, dtype, self.device, self)
+
+    def destroy(self):
+        self.mcx.destroy()
 
 
 class TorchrunCluster(object):
-    """One process per GPU (launched by torchrun / tfrun): rank r is worker r on
-    GPU r and also hosts the PS shards pinned to GPU r.  Handle blobs are
-    exchanged once with all_gather_object -- torch.distributed is plumbing only;
-    nothing on the push/apply/pull path touches NCCL."""
+    """One process per GPU (launched by torchrun / tfrun).  By default rank r is
+    worker r on GPU r and also hosts the PS shards pinned to GPU r; ``ps_ranks`` /
+    ``worker_ranks`` give other shapes (PS shards on GPUs that host no worker,
+    idle ranks).  Handle blobs are exchanged once with all_gather_object --
+    torch.distributed is plumbing only; nothing on the push/apply/pull path
+    touches NCCL.
+
+    path: "staged" (push kernel -> landing slot, reduce+apply kernel, pull kernel),
+          "fused"  (one PS-side kernel gathers over P2P loads, applies, scatters
+                    with P2P stores -- psx_round),
+          "nvls"   (the same kernel with the gather done by the switch --
+                    multimem.ld_reduce -- and the scatter by multimem.st).
+    device: physical CUDA ordinal of this rank (default: its rank); ranks may share
+    a GPU (tests on a 1-GPU box)."""
 
     def __init__(self, variables, ps_tasks, optimizer, placement=None, stripes=None,
-                 fused=False, wire=psx.F32, device=None):
+                 fused=False, wire=psx.F32, device=None, ps_ranks=None, worker_ranks=None,
+                 path=None):
         import torch
         import torch.distributed as dist
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_initialized() else 1
         self.device = self.rank if device is None else device
+        if path is None:
+            path = "fused" if fused else "staged"
+        assert path in ("staged", "fused", "nvls"), path
+        self.path = path
+        self.nvls = path == "nvls"
+        self.fused = fused = path in ("fused", "nvls")
         psx.init(self.device)
         self.layout = VariableLayout(variables, ps_tasks, placement)
         # more stripes than GPUs gives several independent shards per GPU (the
         # pipelining granularity of round_host)
-        self.topo = torchrun_topology(self.layout, self.world, stripes)
-        self.fused = fused
+        self.topo = torchrun_topology(self.layout, self.world, stripes, ps_ranks, worker_ranks)
+        self.worker_ranks = list(self.topo.worker_devices)
+        self.n_workers = len(self.worker_ranks)
+        self.worker_index = (self.worker_ranks.index(self.rank)
+                             if self.rank in self.worker_ranks else None)
         self.servers = OrderedDict()
-        for spec in self.topo.shards_on(self.device):
-            self.servers[spec.key] = ParameterServer(spec, optimizer, self.world, wire,
-                                                     landing_slots=not fused)
+        for spec in self.topo.shards_on(self.rank):
+            self.servers[spec.key] = ParameterServer(spec, optimizer, self.n_workers, wire,
+                                                     landing_slots=not fused,
+                                                     device=self.device)
         handles = self._merge({k: ps.handle() for k, ps in self.servers.items()})
-        self.worker = Worker(self.rank, self.topo, handles, exportable=fused, wire=wire)
-        clients = self._merge({(k, self.rank): h
-                               for k, h in self.worker.client_handles().items()})
+        self.arena = None
+        if self.nvls:
+            if self.worker_ranks != list(range(self.world)) or wire != psx.F32:
+                raise RuntimeError("the NVLS round needs every rank to be a worker (all "
+                                   "members contribute to multimem.ld_reduce) and an f32 wire")
+            esize = 4
+            need = sum(2 * _round_up(_round_up(sum(s.nelem for s in self.topo.shards_of(t)),
+                                               STRIPE_ALIGN) * esize, 4096)
+                       for t in range(self.layout.ps_tasks))
+            self.arena = McArena(self.device, need, self.rank, self.world, self._bcast)
+            self.barrier()                 # every member added its device ...
+            self.arena.bind()              # ... before anyone binds memory
+            self.barrier()
+        self.worker = None
+        self.mailbox = None
+        if self.worker_index is not None:
+            self.worker = Worker(self.worker_index, self.topo, handles,
+                                 exportable=fused and not self.nvls, wire=wire,
+                                 device=self.device, arena=self.arena)
+        clients = self._merge({(k, self.worker_index): h
+                               for k, h in (self.worker.client_handles().items()
+                                            if self.worker else [])})
         for (key, widx), h in clients.items():
             if key in self.servers:
                 self.servers[key].shard.register_client(widx, h)
         # counter rendez-vous: one mailbox per worker, bumped by every shard's apply
-        self.mailbox = psx.Mailbox(self.device)
-        boxes = self._merge({self.rank: self.mailbox.export()})
+        if self.worker is not None:
+            self.mailbox = psx.Mailbox(self.device)
+        boxes = self._merge({self.worker_index: self.mailbox.export()}
+                            if self.worker else {})
         for ps in self.servers.values():
             for widx, h in boxes.items():
                 ps.shard.register_mailbox(widx, h)
         self.n_shards = len(self.topo.shards)
         # counted rendez-vous invariant: between rounds a worker's mailbox holds
         # n_shards (the completions of the previous round, not yet consumed)
-        self.mailbox.set(self.n_shards)
-        if fused:
-            bufs = self._merge({self.rank: self.worker.buffer_handles()})
+        if self.mailbox is not None:
+            self.mailbox.set(self.n_shards)
+        if self.nvls:
             for key, ps in self.servers.items():
-                for widx in range(self.world):
+                goff, poff = self.worker.arena_offsets[ps.spec.task]
+                ps.shard.round_bind_mc(self.arena.mcx, goff, poff, ps.spec.off, self.n_workers)
+        elif fused:
+            bufs = self._merge({self.worker_index: self.worker.buffer_handles()}
+                               if self.worker else {})
+            for key, ps in self.servers.items():
+                for widx in range(self.n_workers):
                     g, p = bufs[widx][ps.spec.task]
                     ps.shard.round_bind(widx, g, p, ps.spec.off)
         self.worker_stream = torch.cuda.Stream(device=self.device)
@@ -442,6 +582,13 @@ class TorchrunCluster(object):
         self.staging = None
         self.h2d_stream = self.d2h_stream = None
         self.barrier()
+
+    def _bcast(self, obj):
+        import torch.distributed as dist
+        box = [obj]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=0)
+        return box[0]
 
     def _merge(self, mine):
         return merge_across_ranks(mine)
@@ -474,12 +621,12 @@ class TorchrunCluster(object):
         ws, pss, wk = self.worker_stream, self.ps_stream, self.worker
         ops = []
         keep = []
-        if self.fused:
+        if wk is not None and self.fused:
             ids = (ctypes.c_uint64 * len(wk.clients))(*[c.id for c in wk.clients.values()])
             keep.append(ids)
             ops.append(dict(op=psx.OP_SIGNAL_COUNTED, ptr=ctypes.addressof(ids), n=len(ids),
                             id=self.mailbox.id, c=self.n_shards, stream=ws))
-        else:
+        elif wk is not None:
             ops.append(dict(op=psx.OP_MAILBOX_CONSUME, id=self.mailbox.id, c=self.n_shards,
                             stream=ws, uses_seq=False))
             for sp in wk.order:
@@ -489,11 +636,12 @@ class TorchrunCluster(object):
                                 n=sp.nelem, a=wk.wire, stream=ws))
         for ps in self.servers.values():
             ops.append(dict(op=psx.OP_ROUND_COUNTED if self.fused else psx.OP_APPLY_COUNTED,
-                            id=ps.shard.id, a=mode, b=0, c=self.world, stream=pss,
+                            id=ps.shard.id, a=mode, b=0, c=self.n_workers, stream=pss,
                             uses_seq=False))
-        ops.append(dict(op=psx.OP_MAILBOX_WAIT, id=self.mailbox.id, c=self.n_shards, stream=ws,
-                        uses_seq=False))
-        if not self.fused:
+        if wk is not None:
+            ops.append(dict(op=psx.OP_MAILBOX_WAIT, id=self.mailbox.id, c=self.n_shards,
+                            stream=ws, uses_seq=False))
+        if wk is not None and not self.fused:
             for sp in wk.order:
                 p = wk.param_flat[sp.task]
                 ops.append(dict(op=psx.OP_PULL, id=wk.clients[sp.key].id,
@@ -521,26 +669,27 @@ class TorchrunCluster(object):
             self._batch(mode).run(self.seq)
             return
         ws, pss, wk = self.worker_stream, self.ps_stream, self.worker
-        if self.fused:
+        if wk is not None and self.fused:
             psx.signal_counted(list(wk.clients.values()), self.seq, self.mailbox,
                                self.n_shards, ws)
-        else:
+        elif wk is not None:
             self.mailbox.consume(self.n_shards, ws)
             wk.push(self.seq, ws)
         for ps in self.servers.values():
             timed = ps is self.dominant
             if timed:       # bracket the kernel alone: do the counted wait by hand first
-                ps.shard.wait_arrivals(self.world, pss)
+                ps.shard.wait_arrivals(self.n_workers, pss)
                 timer.start(pss)
             if self.fused:
-                ps.shard.round_counted(mode, 0, self.world, pss)
+                ps.shard.round_counted(mode, 0, self.n_workers, pss)
             else:
-                ps.shard.apply_counted(mode, 0, self.world, pss)
+                ps.shard.apply_counted(mode, 0, self.n_workers, pss)
             if timed:
                 timer.stop(pss)
-        self.mailbox.wait(self.n_shards, ws)
-        if not self.fused:
-            wk.pull(0, ws)
+        if wk is not None:
+            self.mailbox.wait(self.n_shards, ws)
+            if not self.fused:
+                wk.pull(0, ws)
 
     def capture_round(self, mode, pre=None):
         """A CUDA graph holding ``pre()`` (e.g. the worker's forward/backward)
@@ -568,6 +717,8 @@ class TorchrunCluster(object):
         to the host (D2H stream).  Both PCIe directions stay busy; with S shards
         per bucket the step costs about (S+1)/S of one direction's transfer."""
         import torch
+        assert self.worker is not None and not self.fused, \
+            "round_host runs on worker ranks of a staged-path cluster"
         if self.staging is None:
             self.staging = HostStaging(self.worker)
         if self.h2d_stream is None:
@@ -595,7 +746,7 @@ class TorchrunCluster(object):
                 wk.clients[sp.key].push(g.data_ptr(), sp.nelem, 0, wk.wire, seq, ws)
                 ps = self.servers.get(sp.key)
                 if ps is not None:
-                    ps.shard.apply_counted(mode, 0, self.world, pss)
+                    ps.shard.apply_counted(mode, 0, self.n_workers, pss)
             if i >= 1:
                 sp = shards[i - 1]
                 p = wk.param_flat[sp.task][sp.off:sp.off + sp.nelem]
@@ -611,12 +762,18 @@ class TorchrunCluster(object):
     def close(self):
         self.barrier()
         self._batches.clear()
-        self.worker.close()
+        if self.worker is not None:
+            self.worker.close()
         self.barrier()
         for ps in self.servers.values():
             ps.close()
         self.servers.clear()
-        self.mailbox.destroy()
+        if self.mailbox is not None:
+            self.mailbox.destroy()
+        self.barrier()
+        if self.arena is not None:
+            self.arena.destroy()
+            self.arena = None
 
 
 class TensorListBinding(object):

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # TFMESOS_PSX_LIB selects another build of the same ABI (kernel A/B experiments)
 LIB_PATH = os.environ.get("TFMESOS_PSX_LIB") or os.path.join(HERE, "lib", "libpsx.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 OPT_SGD, OPT_ADAM = 0, 1
 MODE_ASYNC_ORDERED, MODE_SUM, MODE_SYNC_MEAN = 0, 1, 2
 F32, BF16 = 0, 1
@@ -95,6 +95,14 @@ SIGNATURES = {
                            ctypes.POINTER(_u64)]),
     "psx_mc_broadcast": (_i32, [_u64, _i32, _vp, _u64, _u64, _vp]),
     "psx_mc_reduce": (_i32, [_u64, _i32, _vp, _u64, _u64, _vp]),
+    "psx_shard_unregister_client": (_i32, [_u64, _i32]),
+    "psx_mcx_create": (_i32, [_i32, _i32, _u64, ctypes.POINTER(_i32), ctypes.POINTER(_u64)]),
+    "psx_mcx_import": (_i32, [_i32, _i32, _u64, _i32, ctypes.POINTER(_u64)]),
+    "psx_mcx_add_device": (_i32, [_u64]),
+    "psx_mcx_bind": (_i32, [_u64, ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                            ctypes.POINTER(_u64)]),
+    "psx_mcx_destroy": (_i32, [_u64]),
+    "psx_round_bind_mc": (_i32, [_u64, _u64, _u64, _u64, _u64, _i32]),
     "psx_batch": (_i32, [ctypes.POINTER(Op), _i32, ctypes.POINTER(_i32)]),
     "psx_launch_count": (_u64, []),
     "psx_shard_ptr": (_i32, [_u64, _i32, ctypes.POINTER(_vp)]),
@@ -223,6 +231,13 @@ class Shard(object):
 
     def register_client(self, slot, client_handle):
         _check(lib().psx_shard_register_client(self.id, int(slot), client_handle))
+
+    def unregister_client(self, slot):
+        _check(lib().psx_shard_unregister_client(self.id, int(slot)))
+
+    def round_bind_mc(self, member, grad_off_bytes, param_off_bytes, elem_off, n_members):
+        _check(lib().psx_round_bind_mc(self.id, member.id, int(grad_off_bytes),
+                                       int(param_off_bytes), int(elem_off), int(n_members)))
 
     def register_mailbox(self, slot, mailbox_handle):
         _check(lib().psx_shard_register_mailbox(self.id, int(slot), mailbox_handle))
@@ -442,6 +457,56 @@ class MulticastBuffer(object):
     def destroy(self):
         if self.id:
             _check(lib().psx_mc_destroy(self.id))
+            self.id = 0
+
+
+def device_tensor(ptr, numel, dtype, device, owner=None):
+    """Zero-copy torch view of raw device memory (kept alive by ``owner``)."""
+    import torch
+    esz = torch.empty(0, dtype=dtype).element_size()
+
+    class _View(object):
+        __cuda_array_interface__ = {"shape": (int(numel) * esz,), "typestr": "|u1",
+                                    "data": (int(ptr), False), "version": 2, "strides": None}
+    v = _View()
+    v.owner = owner
+    return torch.as_tensor(v, device="cuda:%d" % device).view(dtype)
+
+
+class McMember(object):
+    """This process's member of a multi-process NVSwitch multicast object
+    (psx_mcx_*).  ``fd`` (creator only) is the descriptor to ship to the other
+    members over an AF_UNIX socket."""
+
+    def __init__(self, mid, device, fd=-1):
+        self.id, self.device, self.fd = mid, int(device), fd
+
+    @classmethod
+    def create(cls, device, n_devices, nbytes):
+        fd, mid = _i32(-1), _u64(0)
+        _check(lib().psx_mcx_create(int(device), int(n_devices), int(nbytes),
+                                    ctypes.byref(fd), ctypes.byref(mid)))
+        return cls(mid.value, device, fd.value)
+
+    @classmethod
+    def import_fd(cls, device, n_devices, nbytes, fd):
+        mid = _u64(0)
+        _check(lib().psx_mcx_import(int(device), int(n_devices), int(nbytes), int(fd),
+                                    ctypes.byref(mid)))
+        return cls(mid.value, device)
+
+    def add_device(self):
+        _check(lib().psx_mcx_add_device(self.id))
+
+    def bind(self):
+        uc, mc, size = _vp(0), _vp(0), _u64(0)
+        _check(lib().psx_mcx_bind(self.id, ctypes.byref(uc), ctypes.byref(mc),
+                                  ctypes.byref(size)))
+        return uc.value, mc.value, size.value
+
+    def destroy(self):
+        if self.id:
+            _check(lib().psx_mcx_destroy(self.id))
             self.id = 0
 
 
