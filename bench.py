@@ -55,9 +55,23 @@ def parse():
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
     p.add_argument("--workload", default="nmf_scaled", choices=sorted(WORKLOADS))
     p.add_argument("--mode", default="sum", choices=sorted(MODES))
-    p.add_argument("--path", default="fused", choices=["staged", "fused"],
+    p.add_argument("--path", default="auto",
+                   choices=["auto", "staged", "fused", "unicast", "nvls"],
                    help="staged = push kernel + apply kernel + pull kernel; "
-                        "fused = one PS-side gather/apply/scatter kernel (psx_round)")
+                        "fused (= unicast) = one PS-side gather/apply/scatter kernel over P2P "
+                        "loads/stores (psx_round); nvls = the same round with the NVSwitch "
+                        "reducing the gather (multimem.ld_reduce) and replicating the scatter "
+                        "(multimem.st); auto = nvls from 4 GPUs when the box supports "
+                        "multicast, else fused")
+    p.add_argument("--ps-ranks", default=None,
+                   help="ranks hosting the PS tasks, e.g. '0,1' (task t on rank t) or "
+                        "'0+1,1+0' (task striped over ranks); default: every bucket striped "
+                        "over all ranks")
+    p.add_argument("--worker-ranks", default=None,
+                   help="ranks running a worker, e.g. '2,3,4,5' (BASELINE config #3 as "
+                        "written: --ps-ranks 0,1 --worker-ranks 2,3,4,5); default: all")
+    p.add_argument("--no-verify", action="store_true",
+                   help="skip the oracle check of what was timed (\"verified\" key)")
     p.add_argument("--stripes", type=int, default=None,
                    help="GPUs each bucket is striped over (default: all)")
     p.add_argument("--wire", default="f32", choices=["f32", "bf16"],
@@ -68,7 +82,8 @@ def parse():
     p.add_argument("--no-mnist", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-elems", type=int, default=100_000_000,
-                   help="CPU arms: parameters per step (divided by the worker count)")
+                   help="CPU arms: parameters per step -- the SAME absolute sample at every "
+                        "N, pushed / pulled by N workers")
     return p.parse_args()
 
 
@@ -176,26 +191,49 @@ class KernelTimer(object):
 
 
 # --------------------------------------------------------------- CPU arms ----
-def cpu_ps(args, steps, warmup):
+def parse_ranks(text):
+    if text is None:
+        return None
+    out = []
+    for part in text.split(","):
+        rs = [int(x) for x in part.split("+")]
+        out.append(rs if len(rs) > 1 else rs[0])
+    return out
+
+
+def n_workers_of(args, world):
+    wr = parse_ranks(args.worker_ranks)
+    return len(wr) if wr is not None else world
+
+
+def cpu_ps(args, rounds=12, warmup=2):
     """The reference's CPU-PS path, best case (oracle/ps_oracle.c
     psx_oracle_cpu_ps_round: memcpy push, Eigen-style threaded apply on the PS
-    host cores, memcpy pull), on a bounded sample of the workload."""
+    host cores, memcpy pull) on a bounded sample of the workload: the SAME number
+    of parameters at every N, pushed and pulled by as many workers as the CUDA arm
+    has.  Persistent pinned thread pool, every range first-touched by its owning
+    thread; the reported time is the MEDIAN round."""
     from oracle import ps_oracle as o
     n_full = n_params(args.workload)
-    W = max(1, args.gpus)           # N GPUs <-> N workers, as on the CUDA arm
-    n = min(n_full, max(1_000_000, args.cpu_sample_elems // W))
+    W = max(1, n_workers_of(args, max(1, args.gpus)))
+    n = min(n_full, max(1_000_000, args.cpu_sample_elems))
     base = o.CpuPsBaseline(n, W, o.ADAM, lr=0.01)
     mode = {"sum": o.SUM, "async": o.ASYNC_ORDERED, "mean": o.SYNC_MEAN}[args.mode]
     threads = 0
     for _ in range(warmup):
         threads = base.round(mode)
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    times = []
+    for _ in range(max(3, rounds)):
+        t0 = time.perf_counter()
         threads = base.round(mode)
-    dt = (time.perf_counter() - t0) / max(1, steps)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    dt = times[len(times) // 2]
     gbs = W * n * 8 / dt / 1e9
-    sample = ("%d of %d parameters (%.1f%%), %d worker, memcpy transport, %d rounds"
-              % (n, n_full, 100.0 * n / n_full, W, steps))
+    sample = ("%d of %d parameters (%.1f%%), %d worker(s), memcpy transport, median of %d "
+              "rounds (min %.1f / max %.1f ms), persistent pool pinned 1 thread/core, "
+              "first-touch by owner" % (n, n_full, 100.0 * n / n_full, W, len(times),
+                                        times[0] * 1e3, times[-1] * 1e3))
     return {"value": gbs, "unit": "GB/s", "cores": int(threads), "kind": "port",
             "sample": sample, "ms_per_step_on_sample": dt * 1e3,
             "host_cores_online": os.cpu_count()}
@@ -206,7 +244,7 @@ def run_reference(args):
     if rank != 0:
         return
     steps, warmup = max(1, args.steps), max(1, args.warmup)
-    cb = cpu_ps(args, steps, warmup)
+    cb = cpu_ps(args, rounds=max(10, steps), warmup=warmup)
     n_full = n_params(args.workload)
     line = {
         "impl": "reference",
@@ -214,7 +252,7 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": cb["ms_per_step_on_sample"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, 1, n_full),
+        "config": workload_config(args, max(1, args.gpus), n_full),
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -228,9 +266,12 @@ def workload_config(args, world, n_full):
     return {"workload": "%s: PS round (push+reduce/apply+pull) over %d f32 parameters, Adam(lr=0.01)"
                         % (args.workload, n_full),
             "discipline": args.mode, "path": args.path, "wire": args.wire,
-            "parallelism": "%d workers (1/GPU), %d ps tasks, buckets striped over %s GPU(s)"
-                           % (world, WORKLOADS[args.workload][1],
-                              args.stripes if args.stripes else world),
+            "parallelism": ("%d workers (1/GPU), %d ps tasks, buckets striped over %s GPU(s)"
+                            % (world, WORKLOADS[args.workload][1],
+                               args.stripes if args.stripes else world))
+                           if not (args.ps_ranks or args.worker_ranks) else
+                           ("%d GPUs: ps tasks on ranks %s, workers on ranks %s"
+                            % (world, args.ps_ranks or "all", args.worker_ranks or "all")),
             "l2": "per-step inputs (%.0f MB of gradients per worker) exceed the 126 MB L2"
                   % (n_full * 4 / 1e6) if n_full * 4 > 126e6 else "L2 flushed between steps"}
 
@@ -349,6 +390,156 @@ def mnist_section(torch, engine, psx, world, rank, dist, model="mlp", steps=100,
     return out
 
 
+# ------------------------------------------------- synthetic data + verification
+def synth_np(idx, seed):
+    """Synthetic gradient element(s) `idx` (global bucket indices, int64) of stream
+    `seed`: exact integer hash -> (-0.01, 0.01).  numpy on the host and torch on
+    any GPU produce the same bits, so what a step consumed can be re-derived
+    anywhere (verification needs no copy of the gradients)."""
+    import numpy as np
+    h = (idx.astype(np.int64) * 2654435761 + seed * 40503 + 12345) & 0xFFFFFF
+    return ((h.astype(np.float32) / np.float32(16777216.0) - np.float32(0.5))
+            * np.float32(0.02)).astype(np.float32)
+
+
+def synth_torch(out, seed):
+    """Fill the 1-D tensor `out` (any float dtype, CUDA or pinned host) with stream
+    `seed`, chunk by chunk (the int64 index temp of a 2e8-element bucket is 1.6 GB)."""
+    import torch
+    dev = out.device if out.is_cuda else torch.device("cpu")
+    scale = torch.tensor(0.02, dtype=torch.float32, device=dev)
+    n, step = out.numel(), 1 << 26
+    for lo in range(0, n, step):
+        hi = min(n, lo + step)
+        idx = torch.arange(lo, hi, dtype=torch.int64, device=dev)
+        h = (idx * 2654435761 + seed * 40503 + 12345) & 0xFFFFFF
+        out[lo:hi].copy_(((h.to(torch.float32) / 16777216.0 - 0.5) * scale).to(out.dtype))
+
+
+def grad_seed(worker_index, task):
+    return 100 + 16 * worker_index + task
+
+
+def verify_cluster(cl, mode_name, wire_name, dist, host=False, samples=1_000_000):
+    """Did the rounds that were just timed compute the right thing?  For every
+    shard hosted here, a strided sample (>= `samples` elements, or the whole
+    shard) of var / m / v plus global_step / beta powers is compared with the
+    oracle (oracle.ps_oracle.CShard) replaying the SAME number of rounds on the
+    same synthetic gradients; every worker's pulled parameters are compared with
+    the owners' oracle values at the same positions.  Bit-exact for the unicast
+    paths; the NVLS path (switch-order summation) is held to |diff| <= 1e-5 with at
+    most 1e-6 of the elements outside (cancellation in the 8-way sum).
+    The oracle is the CHECKER here, outside every timed region."""
+    import numpy as np
+    import torch
+    from oracle import ps_oracle as o
+    from tfmesos_b200 import psx
+    omode = {"sum": o.SUM, "async": o.ASYNC_ORDERED, "mean": o.SYNC_MEAN}[mode_name]
+    rounds, W = cl.seq, cl.n_workers
+    exact = not cl.nvls or W <= 2
+    cl.barrier()
+    checked = mism = 0
+    max_diff = 0.0
+    notes = []
+
+    def compare(got, want):
+        nonlocal checked, mism, max_diff
+        checked += want.size
+        if got.dtype != np.float32:                     # bf16 bit patterns
+            mism += int(np.count_nonzero(got != want))
+            return
+        if exact:
+            mism += int(np.count_nonzero(got.view(np.uint32) != want.view(np.uint32)))
+        else:
+            d = np.abs(got.astype(np.float64) - want)
+            max_diff = max(max_diff, float(d.max()) if d.size else 0.0)
+            mism += int(np.count_nonzero(d > 1e-5))
+
+    mine = {}
+    for key, ps in cl.servers.items():
+        sp = ps.spec
+        stride = max(1, sp.nelem // samples)
+        idx = np.arange(0, sp.nelem, stride, dtype=np.int64)
+        slots = np.empty((W, idx.size), np.float32)
+        for w in range(W):
+            g = synth_np(idx + sp.off, grad_seed(w, sp.task))
+            if wire_name == "bf16":
+                g = o.bf16_to_f32(o.f32_to_bf16(g))
+            slots[w] = g
+        ref = o.CShard(idx.size, o.ADAM, lr=0.01)
+        for _ in range(rounds):
+            ref.round(slots, omode)
+        compare(ps.shard.get_values(psx.VAR)[idx], ref.var)
+        compare(ps.shard.get_values(psx.M)[idx], ref.m)
+        compare(ps.shard.get_values(psx.V)[idx], ref.v)
+        st = ps.shard.state()
+        want_step = rounds * (W if mode_name == "async" else 1)
+        if st["global_step"] != want_step or ref.step != want_step:
+            mism += 1
+            notes.append("shard %r global_step %d, expected %d" % (key, st["global_step"], want_step))
+        if np.float32(st["beta1_power"]) != ref.b1p or np.float32(st["beta2_power"]) != ref.b2p:
+            mism += 1
+            notes.append("shard %r beta powers differ" % (key,))
+        mine[key] = (stride, o.f32_to_bf16(ref.var) if wire_name == "bf16" else ref.var)
+    table = [None] * cl.world
+    if cl.world > 1:
+        dist.all_gather_object(table, mine)
+    else:
+        table = [mine]
+    want = {}
+    for d in table:
+        want.update(d)
+    if cl.worker is not None:
+        for sp in cl.topo.shards:
+            stride, ref_var = want[sp.key]
+            src = cl.staging.param[sp.task] if host else cl.worker.param_flat[sp.task]
+            got = src[sp.off:sp.off + sp.nelem][::stride]
+            if wire_name == "bf16":
+                got = got.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+            else:
+                got = got.cpu().numpy()
+            compare(got, ref_var)
+    tot = torch.tensor([checked, mism], dtype=torch.float64)
+    mx = torch.tensor([max_diff], dtype=torch.float64)
+    if cl.world > 1:
+        dist.all_reduce(tot)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    checked, mism = int(tot[0].item()), int(tot[1].item())
+    ok = mism == 0 if exact else mism <= 1e-6 * checked
+    out = {"ok": bool(ok), "rounds_replayed": rounds, "elements_checked": checked,
+           "mismatches": mism,
+           "bar": "bit-exact vs oracle (var, m, v, beta powers, global_step, pulled params)"
+                  if exact else "|diff| <= 1e-5 vs oracle, <= 1e-6 of elements outside "
+                                "(NVLS: switch-order summation)"}
+    if not exact:
+        out["max_abs_diff"] = mx.item()
+    if notes:
+        out["notes"] = notes[:4]
+    return out
+
+
+def resolve_path(args, world, psx, local_rank):
+    if args.path in ("staged", "nvls"):
+        return args.path
+    if args.path in ("fused", "unicast"):
+        return "fused"
+    symmetric = not (args.ps_ranks or args.worker_ranks)
+    if world >= 4 and symmetric and args.wire == "f32" and args.mode != "async":
+        try:
+            if psx.nvls_supported(local_rank):
+                return "nvls"
+        except RuntimeError:
+            pass
+    return "fused"
+
+
+def nvlink_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "nvlink_peaks.json")))
+    except Exception:
+        return {}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -371,16 +562,25 @@ def run_b200(args):
     mode = MODES[args.mode]
     variables, ps_tasks, placement = WORKLOADS[args.workload]
     n_full = n_params(args.workload)
+    path = resolve_path(args, world, psx, local_rank)
+    ps_ranks, worker_ranks = parse_ranks(args.ps_ranks), parse_ranks(args.worker_ranks)
 
     wire = psx.BF16 if args.wire == "bf16" else psx.F32
     esz = 2 if args.wire == "bf16" else 4
-    cl = engine.TorchrunCluster(variables, ps_tasks, engine.AdamOptimizer(0.01),
-                                placement=placement, stripes=args.stripes,
-                                fused=(args.path == "fused"), wire=wire, device=local_rank)
-    gen = torch.Generator(device="cuda").manual_seed(100 + rank)
-    for t in cl.worker.grad_flat:
-        t.copy_(torch.randn(t.numel(), device="cuda", generator=gen) * 1e-2)
-    torch.cuda.synchronize()
+
+    def make_cluster(which, stripes):
+        cl_ = engine.TorchrunCluster(variables, ps_tasks, engine.AdamOptimizer(0.01),
+                                     placement=placement, stripes=stripes, wire=wire,
+                                     device=local_rank, path=which, ps_ranks=ps_ranks,
+                                     worker_ranks=worker_ranks)
+        if cl_.worker is not None:
+            for t, g in enumerate(cl_.worker.grad_flat):
+                synth_torch(g, grad_seed(cl_.worker.index, t))
+        torch.cuda.synchronize()
+        return cl_
+
+    cl = make_cluster(path, args.stripes)
+    W = cl.n_workers
 
     # L2 flush buffer for workloads smaller than L2
     flush = None
@@ -401,10 +601,12 @@ def run_b200(args):
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
         launches0 = psx.launch_count()
-        ev0.record(cl.worker_stream)
+        # a PS-only rank has no worker stream activity: time its PS stream instead
+        st = cl.worker_stream if cl.worker is not None else cl.ps_stream
+        ev0.record(st)
         for _ in range(n_steps):
             one_step(timer, host)
-        ev1.record(cl.worker_stream)
+        ev1.record(st)
         cl.barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64)
         launches = torch.tensor([psx.launch_count() - launches0], dtype=torch.float64)
@@ -420,8 +622,9 @@ def run_b200(args):
         sampler.start()
     timer = KernelTimer()
     ms_step, launches = timed(steps, timer=timer)
-    bytes_step = world * n_full * 2 * esz       # W * N * (s_g + s_p)
+    bytes_step = W * n_full * 2 * esz           # W * N * (s_g + s_p)
     value = bytes_step / (ms_step * 1e-3) / 1e9
+    verified = None if args.no_verify else verify_cluster(cl, args.mode, args.wire, dist)
 
     # dominant kernel: the fused reduce+apply (or gather/apply/scatter) kernel
     peaks = {}
@@ -431,24 +634,34 @@ def run_b200(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    dom = cl.dominant
-    shard_elems = ((dom.spec.nelem + 1023) // 1024) * 1024 if dom is not None else 0
-    k_ms = timer.mean_ms()
-    if args.path == "fused":
-        per_elem = 24 + esz * world + esz * world  # var/m/v r+w, W gradient reads, W param writes
+    # the kernel timer lives on the rank that hosts the largest shard; ranks without
+    # one (worker-only) contribute nothing
+    k_ms = timer.mean_ms() or 0.0
+    shard_elems = ((cl.dominant.spec.nelem + 1023) // 1024) * 1024 if cl.dominant else 0
+    if world > 1:
+        # report the SLOWEST rank's dominant kernel (and its shard size)
+        pair = torch.tensor([k_ms, float(shard_elems)], dtype=torch.float64)
+        allp = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allp, pair)
+        k_ms, shard_elems = max((p[0].item(), int(p[1].item())) for p in allp)
+    if path == "nvls":
+        per_elem = 24 + esz + esz              # var/m/v r+w, ONE reduced gradient in, ONE multicast store out
+        kname = "k_round_mc<ADAM,%s> (multimem.ld_reduce + multimem.st)" % args.mode
+    elif path == "fused":
+        per_elem = 24 + esz * W + esz * W      # var/m/v r+w, W gradient reads, W param writes
         kname = "k_apply<ADAM,%s,SCATTER,PeerSrc<%s>>" % (args.mode, args.wire)
     else:
-        per_elem = 24 + esz * world                # var/m/v r+w, W landing-slot reads
+        per_elem = 24 + esz * W                # var/m/v r+w, W landing-slot reads
         kname = "k_apply<ADAM,%s,SlotSrc<%s>>" % (args.mode, args.wire)
     roofline = None
     if k_ms:
-        # the timer brackets the launches over this rank's largest shard only
+        # the timer brackets the launches over the largest shard only
         bytes_per_launch = per_elem * shard_elems
         achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
-            traffic = tr.get("%s/%s/n%d" % (args.workload, args.path, world))
+            traffic = tr.get("%s/%s/n%d" % (args.workload, path, world))
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak,
@@ -457,42 +670,75 @@ def run_b200(args):
                     "algorithmic_bytes_per_elem": per_elem,
                     "algorithmic_bytes_per_launch": bytes_per_launch,
                     "launches_timed": len(timer.pairs)}
-        if world > 1 and args.path == "fused":
-            # the one-shot kernel is bound by this GPU's NVLink port, not by HBM:
-            # per direction it carries (N-1) remote gradient stripes in + the
-            # other owners' parameter stripes in (and the mirror image out)
-            nvl_bytes = 2 * (world - 1) * shard_elems * esz
+        n_ps_gpus = len({s_.device for s_ in cl.topo.shards})
+        if world > 1 and path in ("fused", "nvls") and n_ps_gpus > 1 or \
+                (world > 1 and path == "fused" and (ps_ranks or worker_ranks)):
+            # bound by this GPU's NVLink port, not by HBM.  Bytes per direction through
+            # the port of the GPU that runs the kernel, while all stripes' kernels run:
+            #   unicast: (W - own) remote gradient stripes in + the other owners'
+            #            parameter stripes in (mirror image out): 2 (N-1) S for the
+            #            symmetric layout, W S for a PS GPU that hosts no worker
+            #   nvls:    N S gradient copies out + S multicast out, S reduced + N S
+            #            parameters in: (N + 1) S
+            S = shard_elems * esz
+            if path == "nvls":
+                nvl_bytes = (world + 1) * S
+            elif ps_ranks or worker_ranks:
+                nvl_bytes = W * S
+            else:
+                nvl_bytes = 2 * (world - 1) * S
             nvl = nvl_bytes / (k_ms * 1e-3) / 1e9
+            pk = nvlink_peaks()
+            duplex = pk.get("duplex_read_write_GBps")
             roofline.update({"bound": "nvlink", "achieved": nvl, "peak": 770.0,
                              "frac": nvl / 770.0,
                              "peak_source": "measured peer copy per direction "
                                             "(B200_PROFILING.md)",
                              "nvlink_bytes_per_direction_per_launch": nvl_bytes,
+                             "frac_of_measured_duplex": (nvl / duplex) if duplex else None,
+                             "measured_duplex_peak": duplex,
+                             "measured_peaks_file": "profiles/nvlink_peaks.json" if pk else None,
+                             "traffic": traffic,
+                             "traffic_note": "NVLink bytes are algorithmic: ncu cannot attach "
+                                             "to a multi-rank run here (profiles/README.md)",
                              "hbm_achieved": achieved, "hbm_frac": achieved / hbm_peak})
+    resolved_stripes = len(cl.topo.shards_of(0))
     cl.close()
 
+    ab = None
+    if path == "nvls" and not args.no_staged:
+        # A/B: the unicast one-kernel round on the same workload
+        cl = make_cluster("fused", args.stripes)
+        for _ in range(warmup):
+            one_step()
+        t3 = KernelTimer()
+        ms_uni, l_uni = timed(max(3, steps // 2), timer=t3)
+        v_uni = None if args.no_verify else verify_cluster(cl, args.mode, args.wire, dist)
+        ab = {"path": "fused (unicast P2P loads/stores)", "value": bytes_step / (ms_uni * 1e-3) / 1e9,
+              "unit": "GB/s", "ms_per_step": ms_uni, "kernel_avg_launch_ms": t3.mean_ms(),
+              "verified": v_uni}
+        cl.close()
+
     staged = None
-    if args.path == "fused" and not args.no_staged:
+    if path != "staged" and not args.no_staged:
         # the three-kernel path (push -> landing slot, reduce+apply, pull), the one
         # asynchronous / cross-process workers use; reported beside the headline
-        cl = engine.TorchrunCluster(variables, ps_tasks, engine.AdamOptimizer(0.01),
-                                    placement=placement, stripes=args.stripes, wire=wire,
-                                    device=local_rank)
-        for t in cl.worker.grad_flat:
-            t.copy_(torch.randn(t.numel(), device="cuda", generator=gen) * 1e-2)
+        cl = make_cluster("staged", args.stripes)
         for _ in range(warmup):
             one_step()
         t2 = KernelTimer()
         ms_staged, l_staged = timed(max(3, steps // 2), timer=t2)
-        se = ((cl.dominant.spec.nelem + 1023) // 1024) * 1024
-        per = 24 + esz * world
+        v_staged = None if args.no_verify else verify_cluster(cl, args.mode, args.wire, dist)
+        per = 24 + esz * W
         staged = {"value": bytes_step / (ms_staged * 1e-3) / 1e9, "unit": "GB/s",
-                  "ms_per_step": ms_staged, "gpu_launches": l_staged,
-                  "apply_kernel": {"kernel": "k_apply<ADAM,%s,SlotSrc<f32>>" % args.mode,
-                                   "avg_launch_ms": t2.mean_ms(),
-                                   "algorithmic_bytes_per_elem": per,
-                                   "achieved": per * se / (t2.mean_ms() * 1e-3) / 1e9,
-                                   "frac": per * se / (t2.mean_ms() * 1e-3) / 1e9 / hbm_peak}}
+                  "ms_per_step": ms_staged, "gpu_launches": l_staged, "verified": v_staged}
+        if t2.mean_ms():
+            se = ((cl.dominant.spec.nelem + 1023) // 1024) * 1024
+            staged["apply_kernel"] = {
+                "kernel": "k_apply<ADAM,%s,SlotSrc<%s>>" % (args.mode, args.wire),
+                "avg_launch_ms": t2.mean_ms(), "algorithmic_bytes_per_elem": per,
+                "achieved": per * se / (t2.mean_ms() * 1e-3) / 1e9,
+                "frac": per * se / (t2.mean_ms() * 1e-3) / 1e9 / hbm_peak}
         cl.close()
 
     e2e = None
@@ -500,21 +746,34 @@ def run_b200(args):
         # same workload through the host-in / host-out public call; more, smaller
         # shards per bucket so H2D, the kernels and D2H pipeline across shards
         e2e_stripes = max(16, world)
-        cl = engine.TorchrunCluster(variables, ps_tasks, engine.AdamOptimizer(0.01),
-                                    placement=placement, stripes=e2e_stripes, wire=wire,
-                                    device=local_rank)
-        cl.staging = engine.HostStaging(cl.worker)
-        for t in cl.staging.grad:
-            t.copy_(torch.randn(t.numel(), generator=torch.Generator().manual_seed(200 + rank))
-                    * 1e-2)
+        cl = make_cluster("staged", e2e_stripes)
+        if cl.worker is not None:
+            cl.staging = engine.HostStaging(cl.worker)
+            for t, g in enumerate(cl.staging.grad):
+                synth_torch(g, grad_seed(cl.worker.index, t))
+
+        def host_step():
+            if cl.worker is not None:
+                cl.round_host(mode)
+            else:                                  # PS-only rank: its applies of this round
+                cl.seq += 1
+                for ps in cl.servers.values():
+                    ps.shard.apply_counted(mode, 0, W, cl.ps_stream)
+
+        _one = one_step
+        one_step = lambda timer=None, host=False: host_step()  # noqa: E731
         for _ in range(2):
-            one_step(host=True)
+            one_step()
         ms_e2e, _ = timed(max(3, steps // 2), host=True)
-        st = cl.staging
+        one_step = _one
+        v_e2e = None if args.no_verify else verify_cluster(cl, args.mode, args.wire, dist,
+                                                           host=True)
+        hb = cl.staging.h2d_bytes() if cl.worker is not None else 0
+        db = cl.staging.d2h_bytes() if cl.worker is not None else 0
         e2e = {"value": bytes_step / (ms_e2e * 1e-3) / 1e9, "unit": "GB/s",
                "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": st.h2d_bytes(), "d2h_bytes_per_step": st.d2h_bytes(),
-               "stripes_per_bucket": e2e_stripes,
+               "h2d_bytes_per_step": hb, "d2h_bytes_per_step": db,
+               "stripes_per_bucket": e2e_stripes, "verified": v_e2e,
                "api": "tfmesos_b200.engine.TorchrunCluster.round_host (pinned host "
                       "gradients in, host parameters out, per rank; H2D / kernels / D2H "
                       "pipelined over the shards)"}
@@ -524,38 +783,46 @@ def run_b200(args):
     clocks = sampler.stop() if rank == 0 else None
 
     mnist = softmax = None
-    if not args.no_mnist:
+    if not args.no_mnist and not (ps_ranks or worker_ranks):
         mnist = mnist_section(torch, engine, psx, world, rank, dist, "mlp")
         softmax = mnist_section(torch, engine, psx, world, rank, dist, "softmax")
 
     cpu = cpu_grpc = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)          # the CPU arm gets every host core
-        cb = cpu_ps(args, steps=5, warmup=1)
+        args.gpus = world
+        cb = cpu_ps(args, rounds=10, warmup=2)
         cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        try:
-            # the same path over the transport the reference actually selects
-            # (protocol='grpc'): loopback gRPC, one RPC per variable per direction
-            from oracle import cpu_ps_grpc
-            cpu_grpc = cpu_ps_grpc.time_round(min(n_full, 10_000_000), steps=3, warmup=1)
-            cpu_grpc.update({"kind": "port", "transport": "python grpcio, loopback, raw bytes "
-                             "(TensorFlow's C++ gRPC core moves tensors a few times faster; "
-                             "the memcpy figure above is the upper bound for this path)"})
-        except Exception as exc:
-            cpu_grpc = {"unavailable": str(exc)[:200]}
+        if world == 1:
+            try:
+                # the same path over the transport the reference actually selects
+                # (protocol='grpc'): loopback gRPC, one RPC per variable per direction
+                from oracle import cpu_ps_grpc
+                cpu_grpc = cpu_ps_grpc.time_round(min(n_full, 10_000_000), steps=3, warmup=1)
+                cpu_grpc.update({"kind": "port", "transport": "python grpcio, loopback, raw "
+                                 "bytes (TensorFlow's C++ gRPC core moves tensors a few times "
+                                 "faster; the memcpy figure above is the upper bound for this "
+                                 "path)"})
+            except Exception as exc:
+                cpu_grpc = {"unavailable": str(exc)[:200]}
 
     if rank == 0:
+        cfg = workload_config(args, world, n_full)
         line = {
             "metric": "ps_push_pull_GBps", "value": value, "unit": "GB/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.wire == "f32" else "f32 master / bf16 wire",
             "data": "synthetic",
-            "config": workload_config(args, world, n_full),
-            "steps_per_sec": 1e3 / ms_step * (world if args.mode == "async" else 1),
+            "config": cfg,
+            "path_resolved": path, "n_workers": W, "stripes_per_bucket": resolved_stripes,
+            "verified": verified["ok"] if verified else None,
+            "verification": verified,
+            "steps_per_sec": 1e3 / ms_step * (W if args.mode == "async" else 1),
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roofline,
+            "unicast_ab": ab,
             "staged_path": staged,
             "e2e": e2e,
             "cpu_baseline": cpu,

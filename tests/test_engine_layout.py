@@ -57,3 +57,27 @@ def test_topology_is_deterministic_and_pins_shards():
     assert [repr(s) for s in t1.shards] == [repr(s) for s in t2.shards]
     assert [(s.task, s.stripe, s.device) for s in t1.shards] == [(0, 0, 0), (0, 1, 1), (1, 0, 1)]
     assert t1.n_workers == 4 and len(t1.shards_on(1)) == 2
+
+
+def test_torchrun_topology_default_and_dedicated_ps_ranks():
+    """Default: every bucket striped over all ranks, worker r on rank r.  Explicit
+    roles: BASELINE config #3 as written -- 2 ps + 4 workers in tfrun's first-fit
+    order (ps tasks first: /root/reference/script/tfrun:58-75, scheduler.py:252-275)."""
+    lay = engine.VariableLayout([("W", (1000, 200)), ("H", (200, 1000))], 2,
+                                placement={"W": 0, "H": 1})
+    t = engine.torchrun_topology(lay, 4)
+    assert [s.device for s in t.shards_of(0)] == [0, 1, 2, 3]
+    assert [s.device for s in t.shards_of(1)] == [1, 2, 3, 0]
+    assert t.worker_devices == [0, 1, 2, 3]
+    d = engine.torchrun_topology(lay, 8, ps_ranks=[0, 1], worker_ranks=[2, 3, 4, 5])
+    assert [(s.task, s.device) for s in d.shards] == [(0, 0), (1, 1)]
+    assert d.worker_devices == [2, 3, 4, 5] and d.n_workers == 4
+    assert d.shards_on(2) == [] and len(d.shards_on(0)) == 1
+    # whole-variable placement AND striping over the two PS GPUs
+    s2 = engine.torchrun_topology(lay, 8, ps_ranks=[[0, 1], [1, 0]], worker_ranks=[2, 3, 4, 5])
+    assert [(s.task, s.stripe, s.device) for s in s2.shards] == \
+        [(0, 0, 0), (0, 1, 1), (1, 0, 1), (1, 1, 0)]
+    # more stripes than listed ranks cycle over them (pipelining granularity)
+    s4 = engine.torchrun_topology(lay, 8, stripes=4, ps_ranks=[[0, 1], [1]],
+                                  worker_ranks=[2, 3])
+    assert [s.device for s in s4.shards_of(0)] == [0, 1, 0, 1]

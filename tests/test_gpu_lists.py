@@ -124,3 +124,41 @@ def test_list_equals_per_variable_push():
         bind.close()
     finally:
         cl.close()
+
+
+@pytest.mark.parametrize("to_shard", [True, False])
+def test_ragged_tensor_first_in_a_list_larger_than_the_ring(to_shard):
+    """Plain (ragged / unaligned) chunks interleaved with TMA chunks in a list big
+    enough that every CTA owns many more chunks than the 4 ring stages: the ring
+    stage and mbarrier phase must follow the count of TMA chunks, not the chunk
+    index (with j-indexed phases this returned stale shared memory or
+    hung).  72 MB list: ragged tensors first, between and after the large ones."""
+    import torch
+    psx.init(0)
+    shapes = [("ragged_first", (4099,)), ("big0", (6_000_000,)), ("odd_mid", (1237,)),
+              ("big1", (6_000_002,)), ("three", (3,)), ("big2", (6_000_001,)), ("tail", (7,))]
+    cl = engine.LocalCluster(shapes, 1, 1, engine.GradientDescentOptimizer(0.1))
+    try:
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        src = {n: torch.randn(s, device="cuda", generator=gen) for n, s in shapes}
+        if to_shard:
+            bind = engine.TensorListBinding(cl.workers[0], src)
+            bind.push(seq=1, tma=True)
+            torch.cuda.synchronize()
+            slot = cl.servers[(0, 0)].shard.get_values(psx.SLOT0)
+            for name, (task, off, shape, numel) in cl.layout.entries.items():
+                want = src[name].cpu().numpy().ravel()
+                assert np.array_equal(slot[off:off + numel].view(np.uint32),
+                                      want.view(np.uint32)), name
+        else:
+            for name, t in src.items():
+                cl.set_variable(name, t.cpu().numpy())
+            dst = {n: torch.full(s, -7.0, device="cuda") for n, s in shapes}
+            bind = engine.TensorListBinding(cl.workers[0], dst)
+            bind.pull(tma=True)
+            torch.cuda.synchronize()
+            for name in src:
+                assert torch.equal(dst[name], src[name]), name
+        bind.close()
+    finally:
+        cl.close()

@@ -8,6 +8,7 @@ One safetensors file per process: every hosted stripe's ``var`` (+ Adam ``m``,
 those bits, so a resumed run continues bit-identically (tests/test_gpu_checkpoint.py).
 """
 import json
+import os
 
 from . import psx
 
@@ -34,7 +35,10 @@ def save(cluster, path, rank=0, world=1):
              "beta1_power": repr(st["beta1_power"]), "beta2_power": repr(st["beta2_power"]),
              "nelem": ps.spec.nelem, "off": ps.spec.off, "opt": ps.shard.opt})
     fn = shard_file(path, rank, world)
-    save_file(tensors, fn, metadata=meta)
+    # write-then-rename (what TF's Saver does): a crash during save never destroys
+    # the previous checkpoint
+    save_file(tensors, fn + ".tmp", metadata=meta)
+    os.replace(fn + ".tmp", fn)
     return fn
 
 

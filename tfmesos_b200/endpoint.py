@@ -42,26 +42,40 @@ def _channel(addr):
     return conn
 
 
+def _drop_channel(addr, conn):
+    _channels.pool.pop(addr, None)
+    try:
+        conn.close()
+    except OSError:
+        pass
+
+
 def call(addr, method, **kw):
     """One request to the endpoint at 'host:port' (accepts 'grpc://host:port',
     the form in ``cluster.targets``, scheduler.py:284)."""
     if addr.startswith('grpc://'):
         addr = addr[len('grpc://'):]
-    for attempt in (0, 1):
+    while True:
+        pool = getattr(_channels, 'pool', None) or {}
+        reused = addr in pool
         conn = _channel(addr)
         try:
             send(conn, (method, kw))
-            status, payload = recv(conn)
-            break
-        except (OSError, AssertionError, EOFError):
-            # stale kept-alive connection (endpoint restarted): reconnect once
-            _channels.pool.pop(addr, None)
-            try:
-                conn.close()
-            except OSError:
-                pass
-            if attempt:
+        except OSError:
+            # the request never left: a stale kept-alive connection (endpoint
+            # restarted).  Reconnect ONCE, and only in this case -- a request that was
+            # delivered is never re-sent (an `apply` would run twice and add a global
+            # step; a recv timeout behind a sync-mode straggler is not a lost request)
+            _drop_channel(addr, conn)
+            if not reused:
                 raise
+            continue
+        try:
+            status, payload = recv(conn)
+        except (OSError, AssertionError, EOFError):
+            _drop_channel(addr, conn)
+            raise
+        break
     if status != 'ok':
         raise RuntimeError('endpoint %s: %s failed: %s' % (addr, method, payload))
     return payload
@@ -121,10 +135,26 @@ class Endpoint(object):
             return self.shards[key][0].export() if key in self.shards else None
 
     def do_register_client(self, key, slot, handle):
-        self.shards[key][0].register_client(slot, handle)
+        # under the lock and with the stream drained: an apply enqueued from another
+        # connection's thread may still hold the mapping this replaces (revived worker)
+        with self.lock:
+            shard = self.shards[key][0]
+            self.stream().synchronize()
+            shard.register_client(slot, handle)
+
+    def do_unregister_client(self, key, slot):
+        """A worker is closing its session: stop publishing into its HBM BEFORE it
+        frees the block (the PS keeps serving the other workers)."""
+        with self.lock:
+            if key in self.shards:
+                self.stream().synchronize()
+                self.shards[key][0].unregister_client(slot)
 
     def do_round_bind(self, key, slot, grad_handle, param_handle, elem_off):
-        self.shards[key][0].round_bind(slot, grad_handle, param_handle, elem_off)
+        with self.lock:
+            shard = self.shards[key][0]
+            self.stream().synchronize()
+            shard.round_bind(slot, grad_handle, param_handle, elem_off)
 
     def do_apply(self, key, mode, first_slot, count, wait_seq, fused=False):
         """Enqueue wait(flags) + the fused reduce/apply kernel on this task's
@@ -168,17 +198,20 @@ class Endpoint(object):
         return view
 
     def do_save(self, path):
+        """One consistent cut: the lock keeps other workers' applies out between the
+        var / m / v / state reads (async training), the stream is drained first."""
         from . import checkpoint
-        self.stream().synchronize()
-        return checkpoint.save(self._as_cluster(), path, self.task_index,
-                               len(self.cluster_def.get('ps', [])) or 1)
+        with self.lock:
+            self.stream().synchronize()
+            return checkpoint.save(self._as_cluster(), path, self.task_index,
+                                   len(self.cluster_def.get('ps', [])) or 1)
 
     def do_restore(self, path):
         from . import checkpoint
-        self.stream().synchronize()
-        fn = checkpoint.restore(self._as_cluster(), path, self.task_index,
-                                len(self.cluster_def.get('ps', [])) or 1)
         with self.lock:
+            self.stream().synchronize()
+            fn = checkpoint.restore(self._as_cluster(), path, self.task_index,
+                                    len(self.cluster_def.get('ps', [])) or 1)
             for entry in self.shards.values():
                 st = entry[0].state()
                 entry[2] = st['global_step']
@@ -208,6 +241,10 @@ class Endpoint(object):
         examples drive their workers this way)."""
         import importlib
         mod, name = fn.split(':')
+        allowed = os.environ.get('TFMESOS_CALL_MODULES', 'examples,tfmesos_b200,tests').split(',')
+        if not any(mod == a or mod.startswith(a + '.') for a in allowed if a):
+            raise PermissionError('module %r is not in TFMESOS_CALL_MODULES (%s)'
+                                  % (mod, ','.join(allowed)))
         return getattr(importlib.import_module(mod), name)(self, **kwargs)
 
     def do_shutdown(self):

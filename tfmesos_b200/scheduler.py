@@ -263,8 +263,8 @@ class TFMesosScheduler(object):
 
     # --------------------------------------------------------- callbacks ----
     def registered(self, driver, framework_id, master_info):
-        logger.info('Tensorflow cluster registered. ( http://%s:%s/#/frameworks/%s )',
-                    master_info.hostname, master_info.port, framework_id.value)
+        logger.info('Tensorflow cluster registered (framework %s, single-box driver)',
+                    framework_id.value)
         if self.containerizer_type is None:
             version = tuple(int(x) for x in driver.version.split('.'))
             self.containerizer_type = 'MESOS' if version >= (1, 0, 0) else 'DOCKER'

@@ -235,4 +235,15 @@ class ParameterClient(object):
         return files
 
     def close(self):
+        """Detach from every PS task first (they stop publishing into this worker's
+        client blocks and drain), only then free the blocks."""
+        import torch
+        self.stream.synchronize()
+        torch.cuda.synchronize(self.device)
+        for spec in self.topo.shards:
+            try:
+                endpoint.call(self.ps_addrs[spec.task], 'unregister_client', key=spec.key,
+                              slot=self.index)
+            except (OSError, RuntimeError, EOFError, AssertionError):
+                pass                      # the PS task is already gone (cluster tear-down)
         self.worker.close()
