@@ -41,6 +41,18 @@ def parse(argv):
     p.add_argument("--batch_size", type=int, default=100)
     p.add_argument("--learning_rate", type=float, default=0.01)
     p.add_argument("--sync_replicas", action="store_true")
+    # B200 build only (not in the reference):
+    p.add_argument("--lag_step", action="store_true",
+                   help="never block the host on the step's global_step: report the newest "
+                        "value already copied back (one step behind)")
+    p.add_argument("--straggler", type=int, default=-1,
+                   help="worker index that sleeps --straggle_ms before every push (makes "
+                        "'whose gradient is stale' deterministic in tests)")
+    p.add_argument("--straggle_ms", type=float, default=400.0)
+    p.add_argument("--device_batches", action="store_true",
+                   help="draw the synthetic batches on the GPU (torch) instead of numpy + H2D")
+    p.add_argument("--quiet_steps", action="store_true",
+                   help="print the per-step line every 100 steps only (timing runs)")
     p.add_argument("--dump", type=str, default=None,
                    help="chief writes the final variables here (.npz), for parity tests")
     return p.parse_args(argv)
@@ -113,22 +125,33 @@ def main(argv):
     print("Training begins @ %f" % time_begin)
     local_step, step = 0, 0
     while step < FLAGS.train_steps:
-        batch_xs = rng.random((FLAGS.batch_size, IMAGE_PIXELS * IMAGE_PIXELS)).astype(np.float32)
-        batch_ys = np.eye(10, dtype=np.float32)[rng.integers(0, 10, FLAGS.batch_size)]
-        x = torch.from_numpy(batch_xs).cuda()
-        y_ = torch.from_numpy(batch_ys).cuda()
+        if FLAGS.device_batches:
+            x = torch.rand(FLAGS.batch_size, IMAGE_PIXELS * IMAGE_PIXELS, device="cuda")
+            y_ = torch.nn.functional.one_hot(
+                torch.randint(0, 10, (FLAGS.batch_size,), device="cuda"), 10).float()
+        else:
+            batch_xs = rng.random((FLAGS.batch_size, IMAGE_PIXELS * IMAGE_PIXELS)).astype(np.float32)
+            batch_ys = np.eye(10, dtype=np.float32)[rng.integers(0, 10, FLAGS.batch_size)]
+            x = torch.from_numpy(batch_xs).cuda()
+            y_ = torch.from_numpy(batch_ys).cuda()
         ps = [sess.params[k].detach().requires_grad_(True) for k in names]
         loss = cross_entropy(ps, x, y_)
         grads = torch.autograd.grad(loss, ps)
         for k, g in zip(names, grads):
             sess.grads[k].copy_(g)
-        step = sess.minimize(mode, FLAGS.replicas_to_aggregate if FLAGS.sync_replicas else None)
+        if FLAGS.straggler == FLAGS.worker_index:
+            torch.cuda.synchronize()
+            time.sleep(FLAGS.straggle_ms / 1e3)
+        step = sess.minimize(mode, FLAGS.replicas_to_aggregate if FLAGS.sync_replicas else None,
+                             fetch_step=not FLAGS.lag_step)
         local_step += 1
-        if is_chief:
+        if is_chief and (not FLAGS.quiet_steps or local_step % 100 == 0):
             print("%f: Worker %d: training step %d done (global step: %d)"
                   % (time.time(), FLAGS.worker_index, local_step, step))
 
+    step = sess.global_step() if FLAGS.lag_step else step
     if is_chief:
+        torch.cuda.synchronize()
         time_end = time.time()
         print("Training ends @ %f" % time_end)
         print("Training elapsed time: %f s" % (time_end - time_begin))

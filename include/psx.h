@@ -272,6 +272,44 @@ int psx_mc_broadcast(uint64_t id, int member, const void *src_dev, uint64_t off_
 int psx_mc_reduce(uint64_t id, int member, void *dst_dev, uint64_t off_bytes, uint64_t nbytes,
                   void *stream);
 
+/* ----------------------------------------- request-free serving (async) --- */
+
+/* The reference's DEFAULT discipline -- every worker's push applied when it
+ * arrives, nobody waits for anybody (examples/mnist/mnist_replica.py:198-205,
+ * examples/mnist/mnist.py:63-72) -- without a host request per step.
+ * psx_serve_start gives the shard a serving loop: one host thread keeps `depth`
+ * iterations of  [stream-wait arrivals >= 1] [k_pick] [k_apply over the picked
+ * slots]  enqueued ahead on the shard's own stream.
+ *   mode PSX_MODE_ASYNC_ORDERED: every unconsumed push found by a pick is applied
+ *     on its own (own beta powers, one global_step each), picks in arrival order,
+ *     slots of one pick in slot order; the worker's client block receives the
+ *     sequence number of its consumed push (psx_wait_applied) and the global_step
+ *     that apply produced (psx_read_step_async).
+ *   mode PSX_MODE_SYNC_MEAN: SyncReplicasOptimizer (mnist_replica.py:109-113,
+ *     148-162) on the device: a push carries the global_step its parameters had
+ *     (psx_push_stamped); older than the shard's global_step = stale = dropped;
+ *     the first `replicas_to_aggregate` fresh ones BY ARRIVAL are averaged and
+ *     applied once; then every registered worker gets a token (psx_wait_tokens),
+ *     fast or slow, like the chief's token queue.
+ * The host accessors (*_values, *_state, set_hyper, (un)register) pause the loop
+ * for their duration; psx_shard_destroy stops it. */
+int psx_serve_start(uint64_t shard_id, int mode, int replicas_to_aggregate, int depth);
+int psx_serve_stop(uint64_t shard_id);
+int psx_serve_stats(uint64_t shard_id, uint64_t *iterations, uint32_t *served, uint32_t *dropped,
+                    int64_t *step);
+/* psx_push that also records `stamp` (low 32 bits of the global_step the gradient
+ * was computed at) for the sync serving mode. */
+int psx_push_stamped(uint64_t client_id, const void *grad_dev, uint64_t off, uint64_t n,
+                     int src_dtype, uint32_t seq, uint32_t stamp, void *stream);
+/* Worker: the stream waits until this worker holds >= target tokens (one per
+ * aggregated apply since the shard was created). */
+int psx_wait_tokens(uint64_t client_id, uint32_t target, void *stream);
+/* Worker: copy the global_step mirrored into this worker's client block by the
+ * apply that consumed its last push into pinned host memory, asynchronously on
+ * `stream` (the value sess.run([train_step, global_step]) returns,
+ * mnist_replica.py:204) -- no host synchronisation. */
+int psx_read_step_async(uint64_t client_id, int64_t *host_pinned, void *stream);
+
 /* Multi-process form (the product runs one process per GPU): one MEMBER per
  * (process, GPU).  The creator makes the multicast object for `n_devices`
  * members and gets its POSIX file descriptor, which the host ships to the other

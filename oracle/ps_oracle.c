@@ -44,6 +44,7 @@
 #define _GNU_SOURCE
 #include <math.h>
 #include <sched.h>
+#include <stdatomic.h>
 #include <stddef.h>
 #include <stdint.h>
 #include <string.h>
@@ -238,10 +239,8 @@ static float synth(size_t i, unsigned seed)
     return ((float)h / 16777216.0f - 0.5f) * 0.02f;
 }
 
-static void cpu_ps_part(cpu_ps_job *j)
+static void cpu_ps_range(cpu_ps_job *j, size_t lo, size_t hi)
 {
-    size_t lo, hi;
-    range_of(j->n, j->part, j->parts, &lo, &hi);
     size_t cnt = hi - lo;
     if (cnt == 0)
         return;
@@ -302,6 +301,34 @@ static void cpu_ps_part(cpu_ps_job *j)
  * (TF's PS runs its Eigen thread pool the same way: long-lived workers, one per
  * core -- tfmesos/server.py:52-61 sizes it from the task's `cpus`.) */
 #define PSX_ORACLE_MAX_THREADS 512
+/* Work distribution: thread p owns range p (the one it first-touched) and walks it
+ * in 64 Ki-element chunks claimed from the range's atomic cursor; a thread that
+ * has finished its own range STEALS chunks from the others' cursors.  On a quiet
+ * box nothing is stolen and every byte stays NUMA-local; when a core is busy with
+ * somebody else's work (the GPU boxes' host cores are shared) its range is
+ * finished by the idle threads instead of stalling the whole round. */
+#define PSX_ORACLE_CHUNK ((size_t)65536)
+typedef struct {
+    _Atomic size_t next;
+    size_t hi;
+    char pad[48];
+} range_cursor;
+static range_cursor g_cursor[PSX_ORACLE_MAX_THREADS];
+
+static void cpu_ps_work(cpu_ps_job *j, int p)
+{
+    for (int k = 0; k < j->parts; ++k) {
+        range_cursor *c = &g_cursor[(p + k) % j->parts];   /* own range first, then steal */
+        for (;;) {
+            size_t lo = atomic_fetch_add_explicit(&c->next, PSX_ORACLE_CHUNK, memory_order_relaxed);
+            if (lo >= c->hi)
+                break;
+            size_t hi = lo + PSX_ORACLE_CHUNK;
+            cpu_ps_range(j, lo, hi < c->hi ? hi : c->hi);
+        }
+    }
+}
+
 static struct {
     int n;
     pthread_t tid[PSX_ORACLE_MAX_THREADS];
@@ -326,8 +353,15 @@ static void *pool_main(void *arg)
             return NULL;
         cpu_ps_job j = g_pool.job;
         j.part = p;
-        if (p < j.parts)
-            cpu_ps_part(&j);
+        if (p < j.parts) {
+            if (j.init) {              /* first touch: strictly the owner, no stealing */
+                size_t lo, hi;
+                range_of(j.n, p, j.parts, &lo, &hi);
+                cpu_ps_range(&j, lo, hi);
+            } else {
+                cpu_ps_work(&j, p);
+            }
+        }
         pthread_barrier_wait(&g_pool.done);
     }
 }
@@ -387,6 +421,12 @@ static int pool_run(const cpu_ps_job *job)
     g_pool.job = *job;
     size_t cap = job->n / 65536 + 1;           /* never less than 64 Ki elements each */
     g_pool.job.parts = (size_t)g_pool.n > cap ? (int)cap : g_pool.n;
+    for (int p = 0; p < g_pool.job.parts; ++p) {
+        size_t lo, hi;
+        range_of(job->n, p, g_pool.job.parts, &lo, &hi);
+        atomic_store_explicit(&g_cursor[p].next, lo, memory_order_relaxed);
+        g_cursor[p].hi = hi;
+    }
     pthread_barrier_wait(&g_pool.start);
     pthread_barrier_wait(&g_pool.done);
     return g_pool.job.parts;

@@ -99,13 +99,15 @@ def test_mnist_replica_sync_replicas_two_workers_matches_oracle(tmp_path):
 
 
 def test_mnist_replica_sync_replicas_to_aggregate_two_of_three(tmp_path):
-    """replicas_to_aggregate < num_workers (mnist_replica.py:64-67,109-113): each
-    round averages 2 of the 3 gradients (workers 0 and 1 in the serialisable
-    schedule), worker 2's is dropped as stale; still one global step per round."""
+    """replicas_to_aggregate < num_workers (mnist_replica.py:64-67,109-113): the PS
+    averages the first 2 gradients to ARRIVE each round and drops the third as
+    stale (device-side SyncReplicas, psx_serve_start SYNC_MEAN).  Worker 2 is made
+    a deliberate straggler (it sleeps before every push), so it is always workers
+    0 and 1 that are aggregated -- the oracle's schedule; one global step per round."""
     dump = str(tmp_path / "final.npz")
     out = tfrun(["-w", "3", "-s", "1"] + replica_cmd(
         ["--train_steps", "6", "--sync_replicas", "--replicas_to_aggregate", "2",
-         "--dump", dump]))
+         "--straggler", "2", "--straggle_ms", "1500", "--dump", dump]))
     assert "global step: 6" in out
     got = np.load(dump)
     want, step = oracle_mnist_replica(3, 6, o.SYNC_MEAN, aggregate=2)

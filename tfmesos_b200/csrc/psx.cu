@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -141,8 +142,10 @@ struct Bound {
     bool valid = false;
 };
 
+struct Server;
 struct Shard {
     int device = 0;
+    Server *server = nullptr;         // request-free serving loop (psx_serve_start)
     Layout lay;
     char *base = nullptr;
     int sm_count = 148;
@@ -310,7 +313,8 @@ inline int grid_for(size_t work_items, int threads, int sm_count, int ctas_per_s
 // dst/src element types resolved at run time -> the four k_copy instances
 int launch_copy(void *dst, int dst_t, const void *src, int src_t, uint64_t n, int sm_count,
                 unsigned int *ticket, unsigned int *flag, uint32_t seq, cudaStream_t st,
-                unsigned int *arrivals = nullptr)
+                unsigned int *arrivals = nullptr, unsigned int *stamp_word = nullptr,
+                uint32_t stamp = 0)
 {
     if (n == 0 && flag == nullptr) return PSX_OK;
     const size_t sb = src_t == PSX_BF16 ? 2 : 4, db = dst_t == PSX_BF16 ? 2 : 4;
@@ -320,7 +324,7 @@ int launch_copy(void *dst, int dst_t, const void *src, int src_t, uint64_t n, in
     const int grid = grid_for(items ? items : 1, kCopyThreads, sm_count, 8);
 #define PSX_COPY(S, D)                                                                        \
     k_copy<S, D><<<grid, kCopyThreads, 0, st>>>((D *)dst, (const S *)src, (size_t)n, vec_ok, \
-                                                 ticket, flag, arrivals, seq)
+                                                 ticket, flag, arrivals, seq, stamp_word, stamp)
     if (src_t == PSX_F32 && dst_t == PSX_F32) PSX_COPY(float, float);
     else if (src_t == PSX_F32 && dst_t == PSX_BF16) PSX_COPY(float, __nv_bfloat16);
     else if (src_t == PSX_BF16 && dst_t == PSX_F32) PSX_COPY(__nv_bfloat16, float);
@@ -407,6 +411,151 @@ int launch_round_mc(Shard *s, int mode, const PeerSet &peers, cudaStream_t st, c
     LAUNCH_CHECK();
     return PSX_OK;
 }
+
+// ------------------------------------------------- request-free serving ----
+// One host thread per served shard keeps `depth` iterations of
+//   cuStreamWaitValue32(arrivals >= 1) ; k_pick ; k_apply<.., PickSrc>
+// enqueued ahead on the shard's own (non-blocking) stream; it sleeps in
+// cudaEventSynchronize (blocking-sync events) while the GPU waits for pushes.
+struct Server {
+    std::thread th;
+    std::atomic<bool> stop{false};
+    cudaStream_t stream = nullptr;
+    int mode = PSX_MODE_ASYNC_ORDERED, aggregate = 1, depth = 8;
+    std::atomic<uint64_t> iterations{0};
+    std::atomic<int> error{0};
+    char errmsg[256] = "";
+};
+
+int serve_iteration(Shard *s, Server *sv)
+{
+    int rc = stream_wait_geq(sv->stream, &s->hdr()->arrivals, 1u);
+    if (rc) return rc;
+    const int n_slots = s->lay.n_slots;
+    if (sv->mode == PSX_MODE_ASYNC_ORDERED)
+        k_pick<PSX_MODE_ASYNC_ORDERED><<<1, 32, 0, sv->stream>>>(s->hdr(), n_slots, 1);
+    else
+        k_pick<PSX_MODE_SYNC_MEAN><<<1, 32, 0, sv->stream>>>(s->hdr(), n_slots, sv->aggregate);
+    LAUNCH_CHECK();
+    PeerSet peers;
+    memset(&peers, 0, sizeof(peers));
+    const ApplyRange r{0, (size_t)s->lay.nelem_pad, 1, 0, 0};
+    if (s->lay.wire == PSX_F32) {
+        PickSrc<float> src{(const float *)s->slot(0), (size_t)s->lay.nelem_pad, nullptr};
+        return launch_apply<false>(s, sv->mode, src, 0, peers, sv->stream, r);
+    }
+    PickSrc<__nv_bfloat16> src{(const __nv_bfloat16 *)s->slot(0), (size_t)s->lay.nelem_pad, nullptr};
+    return launch_apply<false>(s, sv->mode, src, 0, peers, sv->stream, r);
+}
+
+void serve_main(Shard *s, Server *sv)
+{
+    cudaSetDevice(s->device);
+    std::vector<cudaEvent_t> ev((size_t)sv->depth);
+    for (auto &e : ev) cudaEventCreateWithFlags(&e, cudaEventBlockingSync | cudaEventDisableTiming);
+    uint64_t it = 0;
+    while (!sv->stop.load()) {
+        if (it >= (uint64_t)sv->depth) cudaEventSynchronize(ev[it % sv->depth]);  // iteration it-depth done
+        if (sv->stop.load()) break;
+        int rc = serve_iteration(s, sv);
+        if (rc) {
+            snprintf(sv->errmsg, sizeof(sv->errmsg), "%s", g_err);
+            sv->error.store(rc);
+            break;
+        }
+        cudaEventRecord(ev[it % sv->depth], sv->stream);
+        ++it;
+        sv->iterations.store(it);
+    }
+    cudaError_t e = cudaStreamSynchronize(sv->stream);    // the release kernel lets the queue drain
+    if (e != cudaSuccess && sv->error.load() == 0) {
+        snprintf(sv->errmsg, sizeof(sv->errmsg), "serving stream: %s", cudaGetErrorString(e));
+        sv->error.store(PSX_ECUDA);
+    }
+    for (auto &e2 : ev) cudaEventDestroy(e2);
+}
+
+int serve_start_impl(Shard *s, int mode, int aggregate, int depth)
+{
+    if (s->server) return fail(PSX_ESTATE, "shard is already being served");
+    if (s->lay.n_slots < 1) return fail(PSX_ESTATE, "serving needs landing slots (n_slots >= 1)");
+    if (mode != PSX_MODE_ASYNC_ORDERED && mode != PSX_MODE_SYNC_MEAN)
+        return fail(PSX_EINVAL, "serve mode must be ASYNC_ORDERED or SYNC_MEAN");
+    if (mode == PSX_MODE_SYNC_MEAN && (aggregate < 1 || aggregate > s->lay.n_slots))
+        return fail(PSX_EINVAL, "replicas_to_aggregate %d outside 1..%d", aggregate, s->lay.n_slots);
+    if (depth < 1) depth = 8;
+    if (depth > 64) depth = 64;
+    int rc = resolve_memops();
+    if (rc) return rc;
+    PSX_DEVICE(s->device);
+    Server *sv = new Server();
+    sv->mode = mode;
+    sv->aggregate = aggregate;
+    sv->depth = depth;
+    cudaError_t e = cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete sv;
+        return fail(PSX_ECUDA, "creating the serving stream: %s", cudaGetErrorString(e));
+    }
+    s->server = sv;
+    sv->th = std::thread(serve_main, s, sv);
+    return PSX_OK;
+}
+
+// Stops the loop and leaves the shard quiescent: queued iterations run through
+// without picking (stop flag + released counter), pushes that arrive meanwhile
+// stay flagged and counted for the next psx_serve_start.
+int serve_stop_impl(Shard *s, int *mode, int *aggregate, int *depth)
+{
+    Server *sv = s->server;
+    if (!sv) return PSX_OK;
+    PSX_DEVICE(s->device);
+    sv->stop.store(true);
+    cudaStream_t side = nullptr;
+    CU_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    k_serve_release<<<1, 1, 0, side>>>(s->hdr());
+    cudaError_t e = cudaStreamSynchronize(side);
+    sv->th.join();
+    if (e == cudaSuccess) {
+        k_serve_reset<<<1, 1, 0, side>>>(s->hdr());
+        e = cudaStreamSynchronize(side);
+    }
+    cudaStreamDestroy(side);
+    cudaStreamDestroy(sv->stream);
+    if (mode) *mode = sv->mode;
+    if (aggregate) *aggregate = sv->aggregate;
+    if (depth) *depth = sv->depth;
+    int err = sv->error.load();
+    char msg[256];
+    snprintf(msg, sizeof(msg), "%s", sv->errmsg);
+    s->server = nullptr;
+    delete sv;
+    if (err) return fail(err, "serving loop failed: %s", msg);
+    if (e != cudaSuccess) return fail(PSX_ECUDA, "stopping the serving loop: %s", cudaGetErrorString(e));
+    return PSX_OK;
+}
+
+// Host accessors drain the device; a served shard always has iterations waiting
+// for pushes, so they pause the loop for their duration instead.
+struct ServePause {
+    Shard *s;
+    bool was = false;
+    int mode = 0, aggregate = 1, depth = 8, rc = PSX_OK;
+    explicit ServePause(Shard *sh) : s(sh)
+    {
+        if (s->server) {
+            was = true;
+            rc = serve_stop_impl(s, &mode, &aggregate, &depth);
+        }
+    }
+    ~ServePause()
+    {
+        if (was && rc == PSX_OK) serve_start_impl(s, mode, aggregate, depth);
+    }
+};
+#define PSX_PAUSE(shard)              \
+    ServePause pause_(shard);         \
+    if (pause_.rc) return pause_.rc
 
 int wait_slots(Shard *s, int first, int count, uint32_t wait_seq, void *stream)
 {
@@ -527,6 +676,7 @@ int psx_shard_destroy(uint64_t id)
         s = it->second;
         g_shards.erase(it);
     }
+    int src = serve_stop_impl(s, nullptr, nullptr, nullptr);
     cudaError_t e = cudaSetDevice(s->device);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();   // a failed kernel surfaces here
     for (int c = 0; c < PSX_MAX_SLOTS; ++c) {
@@ -542,7 +692,7 @@ int psx_shard_destroy(uint64_t id)
         cudaGetLastError();
         return fail(PSX_ECUDA, "destroying shard %llu: %s", (unsigned long long)id, cudaGetErrorString(e));
     }
-    return PSX_OK;
+    return src;
 }
 
 int psx_shard_export(uint64_t id, void *out_handle)
@@ -572,6 +722,7 @@ int psx_shard_set_hyper(uint64_t id, const float *hyper)
 {
     Shard *s = find(g_shards, id);
     if (!s || !hyper) return fail(PSX_EINVAL, "unknown shard id or null hyper");
+    PSX_PAUSE(s);
     PSX_DEVICE(s->device);
     CU_TRY(cudaDeviceSynchronize());   // not under a running apply
     CU_TRY(cudaMemcpy(&s->hdr()->lr, hyper, 4 * sizeof(float), cudaMemcpyHostToDevice));
@@ -602,6 +753,7 @@ int psx_set_values(uint64_t id, int which, const float *host, uint64_t off, uint
     int rc = region_of(s, which, &base, &dt);
     if (rc) return rc;
     if (n == 0) return PSX_OK;
+    PSX_PAUSE(s);
     PSX_DEVICE(s->device);
     // synchronous by contract: kernels on non-blocking streams are not ordered
     // against the legacy stream's memcpy, so drain the device first
@@ -633,6 +785,7 @@ int psx_get_values(uint64_t id, int which, float *host, uint64_t off, uint64_t n
     int rc = region_of(s, which, &base, &dt);
     if (rc) return rc;
     if (n == 0) return PSX_OK;
+    PSX_PAUSE(s);
     PSX_DEVICE(s->device);
     CU_TRY(cudaDeviceSynchronize());
     if (dt == PSX_F32) {
@@ -654,6 +807,7 @@ int psx_get_state(uint64_t id, float *b1p, float *b2p, int64_t *step, uint32_t *
 {
     Shard *s = find(g_shards, id);
     if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    PSX_PAUSE(s);
     PSX_DEVICE(s->device);
     CU_TRY(cudaDeviceSynchronize());
     ShardHeader h;
@@ -669,6 +823,7 @@ int psx_set_state(uint64_t id, float b1p, float b2p, int64_t step)
 {
     Shard *s = find(g_shards, id);
     if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    PSX_PAUSE(s);
     PSX_DEVICE(s->device);
     CU_TRY(cudaDeviceSynchronize());
     ShardHeader h;
@@ -771,14 +926,22 @@ int psx_shard_register_client(uint64_t shard_id, int slot, const void *client_ha
     int rc = check_blob(client_handle, KIND_CLIENT, &b);
     if (rc) return rc;
     if (s->mirror[slot]) {   // re-registration (a revived worker): nothing in flight may
-        PSX_DEVICE(s->device);   // still hold the old mapping
+        PSX_PAUSE(s);            // still hold the old mapping
+        PSX_DEVICE(s->device);
         CU_TRY(cudaDeviceSynchronize());
         s->mirror[slot] = nullptr;
+        unsigned long long zero = 0;
+        CU_TRY(cudaMemcpy(&s->hdr()->client_block[slot], &zero, sizeof(zero), cudaMemcpyHostToDevice));
         close_mapped(s->client_map[slot]);
     }
     rc = open_blob(b, s->device, &s->client_map[slot]);
     if (rc) return rc;
     s->mirror[slot] = &((ClientBlock *)s->client_map[slot].base)->applied;
+    {   // the served epilogue finds the block through the header, at run time
+        PSX_DEVICE(s->device);
+        unsigned long long addr = (unsigned long long)(uintptr_t)s->client_map[slot].base;
+        CU_TRY(cudaMemcpy(&s->hdr()->client_block[slot], &addr, sizeof(addr), cudaMemcpyHostToDevice));
+    }
     return PSX_OK;
 }
 
@@ -792,9 +955,12 @@ int psx_shard_unregister_client(uint64_t shard_id, int slot)
     Shard *s = find(g_shards, shard_id);
     if (!s) return fail(PSX_EINVAL, "unknown shard id");
     if (slot < 0 || slot >= PSX_MAX_SLOTS) return fail(PSX_EINVAL, "slot %d out of range", slot);
+    PSX_PAUSE(s);
     PSX_DEVICE(s->device);
     CU_TRY(cudaDeviceSynchronize());
     s->mirror[slot] = nullptr;
+    unsigned long long zero = 0;
+    CU_TRY(cudaMemcpy(&s->hdr()->client_block[slot], &zero, sizeof(zero), cudaMemcpyHostToDevice));
     close_mapped(s->client_map[slot]);
     s->mailbox[slot] = nullptr;
     close_mapped(s->mailbox_map[slot]);
@@ -1082,6 +1248,76 @@ int psx_wait_applied(uint64_t client_id, uint32_t seq, void *stream)
     if (!c) return fail(PSX_EINVAL, "unknown client id");
     PSX_DEVICE(c->device);
     return stream_wait_geq(stream, &c->block->applied, seq);
+}
+
+// ------------------------------------------------ request-free serving ABI --
+int psx_serve_start(uint64_t shard_id, int mode, int replicas_to_aggregate, int depth)
+{
+    Shard *s = find(g_shards, shard_id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    return serve_start_impl(s, mode, replicas_to_aggregate, depth);
+}
+
+int psx_serve_stop(uint64_t shard_id)
+{
+    Shard *s = find(g_shards, shard_id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    return serve_stop_impl(s, nullptr, nullptr, nullptr);
+}
+
+int psx_serve_stats(uint64_t shard_id, uint64_t *iterations, uint32_t *served, uint32_t *dropped,
+                    int64_t *step)
+{
+    Shard *s = find(g_shards, shard_id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    if (iterations) *iterations = s->server ? s->server->iterations.load() : 0;
+    PSX_DEVICE(s->device);
+    // a plain copy on its own stream: does not wait for the queued iterations
+    cudaStream_t side = nullptr;
+    CU_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    ShardHeader h;
+    cudaError_t e = cudaMemcpyAsync(&h, s->base, sizeof(h), cudaMemcpyDeviceToHost, side);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(side);
+    cudaStreamDestroy(side);
+    if (e != cudaSuccess) return fail(PSX_ECUDA, "reading serve stats: %s", cudaGetErrorString(e));
+    if (served) *served = h.served;
+    if (dropped) *dropped = h.dropped;
+    if (step) *step = h.step;
+    return PSX_OK;
+}
+
+int psx_push_stamped(uint64_t client_id, const void *grad_dev, uint64_t off, uint64_t n,
+                     int src_dtype, uint32_t seq, uint32_t stamp, void *stream)
+{
+    Client *c = find(g_clients, client_id);
+    if (!c) return fail(PSX_EINVAL, "unknown client id");
+    if (c->lay.n_slots == 0) return fail(PSX_ESTATE, "shard was created without gradient slots");
+    if (off + n > c->lay.nelem) return fail(PSX_EINVAL, "push range outside shard");
+    if (n && !grad_dev) return fail(PSX_EINVAL, "null gradient pointer");
+    if (!seq) return fail(PSX_EINVAL, "a stamped push publishes: seq must be non-zero");
+    PSX_DEVICE(c->device);
+    char *dst = c->my_slot() + off * c->lay.wire_bytes();
+    return launch_copy(dst, c->lay.wire, grad_dev, src_dtype, n, c->sm_count, &c->block->ticket,
+                       &c->hdr()->slot_seq[c->slot], seq, (cudaStream_t)stream, &c->hdr()->arrivals,
+                       &c->hdr()->slot_stamp[c->slot], stamp);
+}
+
+int psx_wait_tokens(uint64_t client_id, uint32_t target, void *stream)
+{
+    Client *c = find(g_clients, client_id);
+    if (!c) return fail(PSX_EINVAL, "unknown client id");
+    PSX_DEVICE(c->device);
+    return stream_wait_geq(stream, &c->block->tokens, target);
+}
+
+int psx_read_step_async(uint64_t client_id, int64_t *host_pinned, void *stream)
+{
+    Client *c = find(g_clients, client_id);
+    if (!c || !host_pinned) return fail(PSX_EINVAL, "unknown client id or null destination");
+    PSX_DEVICE(c->device);
+    CU_TRY(cudaMemcpyAsync(host_pinned, &c->block->step, sizeof(int64_t), cudaMemcpyDeviceToHost,
+                           (cudaStream_t)stream));
+    return PSX_OK;
 }
 
 // ----------------------------------------------------------- tensor lists ---

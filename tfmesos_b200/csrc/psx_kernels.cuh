@@ -15,6 +15,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "psx.h"
@@ -35,6 +36,22 @@ struct ShardHeader {
     unsigned int slot_seq[PSX_MAX_SLOTS];  // round number last pushed into slot s
     unsigned int arrivals;            // +1 per completed push / signal (any slot): lets the
                                       // PS wait for "all W workers of round r" with ONE memop
+    // ---- request-free serving (psx_serve_start): the PS consumes pushes as they ARRIVE
+    unsigned int stop;                // set by psx_serve_stop: queued iterations pick nothing
+    unsigned int pick_n;              // slots the current iteration's apply consumes ...
+    unsigned int pick[PSX_MAX_SLOTS]; // ... in this order (arrival order between picks)
+    unsigned int pick_seq[PSX_MAX_SLOTS];   // push sequence number consumed per picked slot
+    unsigned int slot_seen[PSX_MAX_SLOTS];  // last push of slot s the picker has looked at
+    unsigned int slot_stamp[PSX_MAX_SLOTS]; // global_step the pushed gradient was computed at
+                                            // (SyncReplicas' local_step, mnist_replica.py:148-154)
+    unsigned int pending[PSX_MAX_SLOTS];    // sync mode: fresh gradient waiting for aggregation
+    unsigned int arrival_rank[PSX_MAX_SLOTS];
+    unsigned int arrival_ctr;
+    unsigned int dropped;             // gradients discarded as stale (sync mode)
+    unsigned int served;              // pushes consumed by applies
+    unsigned long long client_block[PSX_MAX_SLOTS];  // PS-side address of each registered worker's
+                                      // ClientBlock (0 = none): read by the served epilogue at RUN
+                                      // time, so a worker may register while iterations are queued
 };
 static_assert(sizeof(ShardHeader) <= 4096, "header must fit its page");
 
@@ -42,9 +59,14 @@ static_assert(sizeof(ShardHeader) <= 4096, "header must fit its page");
 // the mirror of the shard's apply_seq the PS writes remotely.
 struct ClientBlock {
     unsigned int ticket;
-    unsigned int applied;             // mirror of ShardHeader::apply_seq
-    unsigned int pad[62];
+    unsigned int applied;             // mirror of ShardHeader::apply_seq; in served mode: the
+                                      // sequence number of THIS worker's last consumed push
+    long long step;                   // served mode: global_step after that apply (what
+                                      // sess.run([train_step, global_step]) returns)
+    unsigned int tokens;              // served sync mode: one token per aggregated apply
+    unsigned int pad[59];
 };
+static_assert(sizeof(ClientBlock) == 256, "client block is 256 bytes");
 
 struct PeerSet {                      // by-value kernel argument (PS address space)
     const void *grad[PSX_MAX_SLOTS];  // bound worker gradient buffers (psx_round), wire dtype
@@ -71,6 +93,19 @@ __device__ __forceinline__ void publish_store(unsigned int *p, unsigned int v)
 __device__ __forceinline__ void publish_add(unsigned int *p, unsigned int v)
 {
     asm volatile("red.relaxed.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// the arrival counter is bumped AFTER the slot flag it announces (release: the flag
+// store above is ordered before it), so a picker woken by the counter finds the flag
+__device__ __forceinline__ void publish_add_release(unsigned int *p, unsigned int v)
+{
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_sys(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 // streaming (read-once) 128-bit load; works on local and peer-mapped addresses
@@ -171,7 +206,8 @@ constexpr int kCopyUnroll = 4;
 template <typename SRC, typename DST>
 __global__ void __launch_bounds__(kCopyThreads)
 k_copy(DST *__restrict__ dst, const SRC *__restrict__ src, size_t n, int vec_ok,
-       unsigned int *ticket, unsigned int *flag, unsigned int *arrivals, unsigned int seq)
+       unsigned int *ticket, unsigned int *flag, unsigned int *arrivals, unsigned int seq,
+       unsigned int *stamp_word = nullptr, unsigned int stamp = 0)
 {
     if (vec_ok) {
         const size_t n4 = n >> 2;
@@ -204,9 +240,10 @@ k_copy(DST *__restrict__ dst, const SRC *__restrict__ src, size_t n, int vec_ok,
     if (flag != nullptr) {
         if (last_cta(ticket) && threadIdx.x == 0) {
             *ticket = 0;
+            if (stamp_word != nullptr) publish_store(stamp_word, stamp);   // ordered by the fence below
             __threadfence_system();
             publish_store(flag, seq);
-            if (arrivals != nullptr) publish_add(arrivals, 1u);
+            if (arrivals != nullptr) publish_add_release(arrivals, 1u);
         }
     }
 }
@@ -492,6 +529,146 @@ __device__ __forceinline__ void finish_apply(ShardHeader *h, const PeerSet &peer
     }
 }
 
+// ---------------------------------------------------- request-free serving ----
+// The reference's default discipline: every worker's push is applied when it
+// ARRIVES and nobody waits for anybody (examples/mnist/mnist_replica.py:198-205,
+// mnist.py:63-72) -- with no host in the loop.  The PS keeps a few iterations of
+//     cuStreamWaitValue32(arrivals >= 1) ; k_pick ; k_apply<.., PickSrc>
+// enqueued ahead on one stream per shard (psx_serve_start).  A push bumps
+// `arrivals`; the wait releases; k_pick (one warp) looks at every slot flag,
+// lists the slots holding an unconsumed push in the header and takes them off the
+// counter; the apply kernel consumes exactly that list in ONE pass (in list order,
+// each with its own beta powers: the serialisable async schedule) and its last CTA
+// tells each consumed worker "your push k is in" (+ the global_step it produced)
+// in that worker's own HBM.  The worker side is push ; stream-wait ; pull.
+//
+// SYNC (SyncReplicasOptimizer, mnist_replica.py:109-113,148-162): a gradient whose
+// stamp (the global_step its parameters had) is older than the shard's global_step
+// is dropped as stale; fresh ones wait as `pending` until R = replicas_to_aggregate
+// of them are there; the first R in ARRIVAL order are averaged and applied once;
+// every worker then receives a token (the chief's token queue), fast or slow.
+template <int MODE>
+__global__ void k_pick(ShardHeader *h, int n_slots, int aggregate)
+{
+    __shared__ unsigned int s_new[PSX_MAX_SLOTS];
+    const int s = threadIdx.x;
+    unsigned int seq = 0;
+    bool fresh = false;
+    const bool stopping = ld_sys(&h->stop) != 0;
+    if (s < n_slots && !stopping) {
+        seq = ld_sys(&h->slot_seq[s]);
+        fresh = seq != h->slot_seen[s];
+    }
+    if (s < PSX_MAX_SLOTS) s_new[s] = fresh ? seq : 0u;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    unsigned int n_new = 0, n_pick = 0;
+    if (MODE == PSX_MODE_ASYNC_ORDERED) {
+        for (int k = 0; k < n_slots; ++k) {
+            if (s_new[k] == 0u) continue;
+            h->slot_seen[k] = s_new[k];
+            h->pick[n_pick] = (unsigned int)k;
+            h->pick_seq[n_pick] = s_new[k];
+            ++n_pick;
+            ++n_new;
+        }
+    } else {
+        const unsigned int step = (unsigned int)h->step;
+        for (int k = 0; k < n_slots; ++k) {
+            if (s_new[k] != 0u) {               // a new push replaces whatever the slot held
+                h->slot_seen[k] = s_new[k];
+                h->pending[k] = 1u;
+                h->arrival_rank[k] = ++h->arrival_ctr;
+                ++n_new;
+            }
+            // stale: computed from parameters older than the current global_step
+            if (h->pending[k] && (int)(ld_sys(&h->slot_stamp[k]) - step) < 0) {
+                h->pending[k] = 0u;
+                ++h->dropped;
+            }
+        }
+        unsigned int n_pending = 0;
+        for (int k = 0; k < n_slots; ++k) n_pending += h->pending[k];
+        if (!stopping && n_pending >= (unsigned int)aggregate) {
+            for (int r = 0; r < aggregate; ++r) {          // the first R by arrival
+                int best = -1;
+                for (int k = 0; k < n_slots; ++k)
+                    if (h->pending[k] && (best < 0 || (int)(h->arrival_rank[k] - h->arrival_rank[best]) < 0))
+                        best = k;
+                h->pending[best] = 0u;
+                h->pick[n_pick] = (unsigned int)best;
+                h->pick_seq[n_pick] = h->slot_seen[best];
+                ++n_pick;
+            }
+        }
+    }
+    h->pick_n = n_pick;
+    if (n_new) atomicSub(&h->arrivals, n_new);
+}
+
+// epilogue of a served apply: per-slot completion instead of the broadcast one
+template <int OPT, int MODE>
+__device__ __forceinline__ void finish_served(ShardHeader *h, int count, float b1, float b2)
+{
+    const bool last = last_cta<false>(&h->ticket);
+    if (!last || threadIdx.x != 0) return;
+    h->ticket = 0;
+    if (count == 0) return;
+    const int applies = (MODE == PSX_MODE_ASYNC_ORDERED) ? count : 1;
+    if (OPT == PSX_OPT_ADAM) {
+        float p1 = h->b1p, p2 = h->b2p;
+        for (int k = 0; k < applies; ++k) {
+            p1 = __fmul_rn(p1, b1);
+            p2 = __fmul_rn(p2, b2);
+        }
+        h->b1p = p1;
+        h->b2p = p2;
+    }
+    const long long step0 = h->step;
+    h->step = step0 + applies;
+    h->served += (unsigned int)count;
+    const unsigned int seq = h->apply_seq + 1;
+    // the step values first, ONE system fence, then the words the workers wait on
+    if (MODE == PSX_MODE_ASYNC_ORDERED) {
+        for (int k = 0; k < count; ++k) {
+            ClientBlock *cb = (ClientBlock *)h->client_block[h->pick[k]];
+            if (cb) cb->step = step0 + k + 1;
+        }
+    } else {
+        for (int c = 0; c < PSX_MAX_SLOTS; ++c) {
+            ClientBlock *cb = (ClientBlock *)h->client_block[c];
+            if (cb) cb->step = step0 + 1;
+        }
+    }
+    __threadfence_system();
+    publish_store(&h->apply_seq, seq);
+    if (MODE == PSX_MODE_ASYNC_ORDERED) {
+        for (int k = 0; k < count; ++k) {
+            ClientBlock *cb = (ClientBlock *)h->client_block[h->pick[k]];
+            if (cb) publish_store(&cb->applied, h->pick_seq[k]);
+        }
+    } else {
+        for (int c = 0; c < PSX_MAX_SLOTS; ++c) {       // a token for EVERY worker
+            ClientBlock *cb = (ClientBlock *)h->client_block[c];
+            if (cb) publish_add(&cb->tokens, 1u);
+        }
+    }
+}
+
+// psx_serve_stop: let every queued iteration run through without picking anything
+__global__ void k_serve_release(ShardHeader *h)
+{
+    h->stop = 1u;
+    __threadfence_system();
+    atomicAdd(&h->arrivals, 1u << 30);
+}
+__global__ void k_serve_reset(ShardHeader *h)
+{
+    atomicSub(&h->arrivals, 1u << 30);      // pushes that came in meanwhile stay counted
+    h->stop = 0u;
+    h->pick_n = 0u;
+}
+
 constexpr int kApplyThreads = 256;
 constexpr int kSlotChunk = 4;  // gradient vectors in flight per thread
 #ifndef PSX_APPLY_MIN_CTAS
@@ -543,6 +720,21 @@ __device__ __forceinline__ void mc_st(float *mc, const float4 &v)
                  "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
+// Served mode: which landing slots this apply consumes was decided by k_pick right
+// before (same stream) and sits in the shard header.
+template <typename WIRE> struct PickSrc {
+    static constexpr bool kPrefetch = false;
+    static constexpr bool kDynamic = true;
+    const WIRE *base;
+    size_t stride;
+    const unsigned int *pick;        // set inside the kernel: the list, staged in shared memory
+    __device__ __forceinline__ float4 load(int s, size_t i) const
+    {
+        return Vec4<WIRE>::load(base + (size_t)pick[s] * stride + 4 * i);
+    }
+};
+template <typename SRC> struct IsDynamic { static constexpr bool value = false; };
+template <typename W> struct IsDynamic<PickSrc<W>> { static constexpr bool value = true; };
 template <typename SRC> struct WireOf { using type = float; };
 template <typename W> struct WireOf<PeerSrc<W>> { using type = W; };
 template <typename SRC> struct IsMulticast { static constexpr bool value = false; };
@@ -555,9 +747,18 @@ k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restric
         float4 *__restrict__ vel, SRC src, int count, size_t n4, PeerSet peers, int finish,
         unsigned int consume, int divisor)
 {
-    // count   = gradient sources read per element (1 on the NVLS path: the switch
-    //           has already summed the workers' copies)
+    // count   = gradient sources read per element; served mode (PickSrc): whatever
+    //           k_pick selected, read from the header (0 = nothing to do this time)
     // divisor = SYNC_MEAN's denominator (the number of workers aggregated)
+    __shared__ unsigned int s_pick[PSX_MAX_SLOTS];
+    if constexpr (IsDynamic<SRC>::value) {
+        count = (int)h->pick_n;
+        divisor = count;
+        if (count == 0) n4 = 0;                 // nothing arrived that can be applied yet
+        if (threadIdx.x < PSX_MAX_SLOTS) s_pick[threadIdx.x] = h->pick[threadIdx.x];
+        src.pick = s_pick;
+        __syncthreads();
+    }
     // counted rendez-vous: the stream waited for arrivals >= consume right before
     // this launch; take them off the counter so the next round waits for the same
     // constant again (that is what makes a round replayable from a CUDA graph).
@@ -674,8 +875,11 @@ k_apply(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__restric
         }
     }
 
-    finish_apply<OPT, IsMulticast<SRC>::value>(h, peers, (MODE == PSX_MODE_ASYNC_ORDERED) ? count : 1,
-                                                finish, b1, b2);
+    if (IsDynamic<SRC>::value)
+        finish_served<OPT, MODE>(h, count, b1, b2);
+    else
+        finish_apply<OPT, IsMulticast<SRC>::value>(h, peers, (MODE == PSX_MODE_ASYNC_ORDERED) ? count : 1,
+                                                    finish, b1, b2);
 }
 
 // ------------------------------------------------------------- NVLS round ----

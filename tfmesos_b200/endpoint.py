@@ -127,7 +127,7 @@ class Endpoint(object):
             if key not in self.shards:
                 lr, b1, b2, eps = hyper
                 shard = psx.Shard(self.device(), nelem, opt, lr, b1, b2, eps, n_slots, wire)
-                self.shards[key] = [shard, 0, 0]
+                self.shards[key] = [shard, 0, 0, None]
             return self.shards[key][0].export()
 
     def do_shard_handle(self, key):
@@ -155,6 +155,43 @@ class Endpoint(object):
             shard = self.shards[key][0]
             self.stream().synchronize()
             shard.round_bind(slot, grad_handle, param_handle, elem_off)
+
+    def do_serve(self, key, mode, replicas_to_aggregate=1, depth=8):
+        """Start the shard's request-free serving loop (psx_serve_start): from now on
+        pushes are consumed as they arrive, with no request per step -- the
+        reference's default discipline (examples/mnist/mnist_replica.py:198-205) or,
+        mode SYNC_MEAN, SyncReplicasOptimizer on the device (:148-162).  Idempotent:
+        every worker asks at its first step, the first one starts it."""
+        with self.lock:
+            entry = self.shards[key]
+            want = (int(mode), int(replicas_to_aggregate))
+            if entry[3] is None:
+                entry[0].serve_start(want[0], want[1], depth)
+                entry[3] = want + (int(depth),)
+            elif entry[3][:2] != want:
+                raise RuntimeError('shard %r is served with mode/aggregate %r, asked for %r'
+                                   % (key, entry[3][:2], want))
+            return True
+
+    def _paused(self):
+        """Context: every served shard's loop stopped (one consistent cut across
+        var / m / v / state), restarted afterwards."""
+        ep = self
+
+        class _P(object):
+            def __enter__(self_):
+                self_.served = [e for e in ep.shards.values() if e[3] is not None]
+                for e in self_.served:
+                    e[0].serve_stop()
+
+            def __exit__(self_, *exc):
+                for e in self_.served:
+                    e[0].serve_start(*e[3])
+                return False
+        return _P()
+
+    def do_serve_stats(self, key):
+        return self.shards[key][0].serve_stats()
 
     def do_apply(self, key, mode, first_slot, count, wait_seq, fused=False):
         """Enqueue wait(flags) + the fused reduce/apply kernel on this task's
@@ -201,14 +238,14 @@ class Endpoint(object):
         """One consistent cut: the lock keeps other workers' applies out between the
         var / m / v / state reads (async training), the stream is drained first."""
         from . import checkpoint
-        with self.lock:
+        with self.lock, self._paused():
             self.stream().synchronize()
             return checkpoint.save(self._as_cluster(), path, self.task_index,
                                    len(self.cluster_def.get('ps', [])) or 1)
 
     def do_restore(self, path):
         from . import checkpoint
-        with self.lock:
+        with self.lock, self._paused():
             self.stream().synchronize()
             fn = checkpoint.restore(self._as_cluster(), path, self.task_index,
                                     len(self.cluster_def.get('ps', [])) or 1)

@@ -103,6 +103,13 @@ SIGNATURES = {
                             ctypes.POINTER(_u64)]),
     "psx_mcx_destroy": (_i32, [_u64]),
     "psx_round_bind_mc": (_i32, [_u64, _u64, _u64, _u64, _u64, _i32]),
+    "psx_serve_start": (_i32, [_u64, _i32, _i32, _i32]),
+    "psx_serve_stop": (_i32, [_u64]),
+    "psx_serve_stats": (_i32, [_u64, ctypes.POINTER(_u64), ctypes.POINTER(_u32),
+                               ctypes.POINTER(_u32), ctypes.POINTER(ctypes.c_int64)]),
+    "psx_push_stamped": (_i32, [_u64, _vp, _u64, _u64, _i32, _u32, _u32, _vp]),
+    "psx_wait_tokens": (_i32, [_u64, _u32, _vp]),
+    "psx_read_step_async": (_i32, [_u64, _vp, _vp]),
     "psx_batch": (_i32, [ctypes.POINTER(Op), _i32, ctypes.POINTER(_i32)]),
     "psx_launch_count": (_u64, []),
     "psx_shard_ptr": (_i32, [_u64, _i32, ctypes.POINTER(_vp)]),
@@ -232,6 +239,20 @@ class Shard(object):
     def register_client(self, slot, client_handle):
         _check(lib().psx_shard_register_client(self.id, int(slot), client_handle))
 
+    def serve_start(self, mode, replicas_to_aggregate=1, depth=8):
+        """Request-free serving loop on this shard (psx_serve_start)."""
+        _check(lib().psx_serve_start(self.id, int(mode), int(replicas_to_aggregate), int(depth)))
+
+    def serve_stop(self):
+        _check(lib().psx_serve_stop(self.id))
+
+    def serve_stats(self):
+        it, served, dropped, step = _u64(0), _u32(0), _u32(0), ctypes.c_int64(0)
+        _check(lib().psx_serve_stats(self.id, ctypes.byref(it), ctypes.byref(served),
+                                     ctypes.byref(dropped), ctypes.byref(step)))
+        return {"iterations": it.value, "served": served.value, "dropped": dropped.value,
+                "global_step": step.value}
+
     def unregister_client(self, slot):
         _check(lib().psx_shard_unregister_client(self.id, int(slot)))
 
@@ -303,6 +324,16 @@ class Client(object):
     def pull(self, param_ptr, n, off=0, dtype=F32, wait_seq=0, stream=None):
         _check(lib().psx_pull(self.id, param_ptr, int(off), int(n), int(dtype),
                               int(wait_seq), _stream_ptr(stream)))
+
+    def push_stamped(self, grad_ptr, n, off=0, dtype=F32, seq=1, stamp=0, stream=None):
+        _check(lib().psx_push_stamped(self.id, grad_ptr, int(off), int(n), int(dtype), int(seq),
+                                      int(stamp) & 0xFFFFFFFF, _stream_ptr(stream)))
+
+    def wait_tokens(self, target, stream=None):
+        _check(lib().psx_wait_tokens(self.id, int(target) & 0xFFFFFFFF, _stream_ptr(stream)))
+
+    def read_step_async(self, host_ptr, stream=None):
+        _check(lib().psx_read_step_async(self.id, host_ptr, _stream_ptr(stream)))
 
     def signal(self, seq, stream=None):
         _check(lib().psx_signal(self.id, int(seq), _stream_ptr(stream)))

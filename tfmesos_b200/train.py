@@ -142,8 +142,12 @@ class ParameterClient(object):
         self.params, self.grads = self.worker.params, self.worker.grads
         self.stream = torch.cuda.Stream(device=device)
         self.push_seq = 0
-        self.step_base = 0            # global_step at session start (after a restore)
-        self.applied = {spec.key: 0 for spec in self.topo.shards}
+        self.serving = None           # (mode, replicas_to_aggregate) once the PS loops run
+        # global_step as mirrored into this worker's HBM by the apply that consumed
+        # its push, copied to pinned host memory on the stream (never a request)
+        self._step_host = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self._step_event = None
+        self._step_client = self.worker.clients[self.topo.shards[0].key]
         if self.is_chief:
             for name, value in (init or {}).items():
                 self.assign(name, value)
@@ -156,6 +160,7 @@ class ParameterClient(object):
                     if time.time() > deadline:
                         raise RuntimeError('chief never initialised the variables')
                     time.sleep(0.05)
+        self._last_step = self.global_step()
         self.pull()
 
     def assign(self, name, value):
@@ -173,51 +178,82 @@ class ParameterClient(object):
                             off=off, n=numel)
         return np.frombuffer(raw, np.float32).reshape(shape).copy()
 
-    def pull(self):
-        """PULL (Variable reads of the next sess.run)."""
+    def _enqueue_pull(self):
         for spec in self.topo.shards:
             p = self.worker.param_flat[spec.task]
             self.worker.clients[spec.key].pull(p.data_ptr() + spec.off * p.element_size(),
-                                               spec.nelem, 0, self.worker.wire,
-                                               self.applied[spec.key], self.stream)
+                                               spec.nelem, 0, self.worker.wire, 0, self.stream)
+
+    def pull(self):
+        """PULL (Variable reads of the next sess.run), synchronously."""
+        self._enqueue_pull()
         self.stream.synchronize()
 
-    def minimize(self, mode=psx.MODE_ASYNC_ORDERED, replicas_to_aggregate=None):
-        """PUSH this worker's gradients and have every PS apply them (async: this
-        worker's slot alone, one global step), then PULL the result -- one
-        ``sess.run([train_step, global_step])`` (mnist_replica.py:204).
+    def _serve(self, mode, aggregate):
+        """First step only: make sure every PS shard runs its serving loop in this
+        discipline (one request per PS task, then never again)."""
+        want = (int(mode), int(aggregate))
+        if self.serving is None:
+            for spec in self.topo.shards:
+                endpoint.call(self.ps_addrs[spec.task], 'serve', key=spec.key, mode=want[0],
+                              replicas_to_aggregate=want[1])
+            self.serving = want
+        elif self.serving != want:
+            raise RuntimeError('this session already trains with mode/aggregate %r' %
+                               (self.serving,))
 
-        Aggregated modes take ``replicas_to_aggregate`` (SyncReplicasOptimizer,
-        mnist_replica.py:109-113,148-154): the round's single apply averages that
-        many gradients and the rest are dropped as stale.  Which ones is decided by
-        arrival order in TensorFlow; here, as in the oracle's serialisable
-        schedule, by worker index (slots 0 .. replicas_to_aggregate-1)."""
+    def _known_step(self):
+        """The newest global_step the host has seen (waits for the last enqueued
+        8-byte copy only if it has not landed yet -- normally it has)."""
+        if self._step_event is not None:
+            self._step_event.synchronize()
+            self._step_event = None
+            self._last_step = int(self._step_host[0])
+        return self._last_step
+
+    def minimize(self, mode=psx.MODE_ASYNC_ORDERED, replicas_to_aggregate=None, fetch_step=True):
+        """One ``sess.run([train_step, global_step])`` (mnist_replica.py:204) with NO
+        request to the PS: PUSH this worker's gradients into its landing slots (the
+        kernel's epilogue bumps each shard's arrival counter), stream-wait until the
+        PS's serving loop has consumed the push, PULL.  The PS applies pushes as
+        they arrive (async, the reference's default), or -- ``mode=MODE_SYNC_MEAN``
+        -- runs SyncReplicasOptimizer on the device: the first
+        ``replicas_to_aggregate`` fresh gradients by ARRIVAL are averaged and
+        applied, later / stale ones dropped, every worker released by a token
+        (mnist_replica.py:109-113,148-162).
+
+        Returns global_step.  fetch_step=True waits for the 8-byte copy of the step
+        this push produced (the value TF returns); fetch_step=False never blocks the
+        host and returns the newest step already known (one step behind)."""
         import torch
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+        if mode == psx.MODE_SUM:
+            raise ValueError('the serving loop applies per push (async) or averages (sync)')
+        aggregate = self.n_workers if replicas_to_aggregate is None \
+            else max(1, min(int(replicas_to_aggregate), self.n_workers))
+        self._serve(mode, aggregate if mode == psx.MODE_SYNC_MEAN else 1)
+        stamp = self._known_step()              # the step our parameters are at
+        cur = torch.cuda.current_stream(self.device)
+        self.stream.wait_stream(cur)
         self.push_seq += 1
-        self.worker.push(self.push_seq, self.stream)
-        step = None
+        wk = self.worker
+        for spec in wk.order:
+            g = wk.grad_flat[spec.task]
+            wk.clients[spec.key].push_stamped(g.data_ptr() + spec.off * g.element_size(),
+                                              spec.nelem, 0, wk.wire, self.push_seq, stamp,
+                                              self.stream)
         for spec in self.topo.shards:
-            if mode == psx.MODE_ASYNC_ORDERED:
-                # this worker's gradient alone: one ApplyAdam, one global step
-                r = endpoint.call(self.ps_addrs[spec.task], 'apply', key=spec.key, mode=mode,
-                                  first_slot=self.index, count=1, wait_seq=self.push_seq)
-                self.applied[spec.key] = r['applied']
-                if spec.key == (0, 0):
-                    step = r['global_step']
+            if mode == psx.MODE_SYNC_MEAN:
+                wk.clients[spec.key].wait_tokens(self.push_seq, self.stream)
             else:
-                # aggregated modes: the chief triggers the single apply of the
-                # round (SyncReplicasOptimizer's chief queue runner,
-                # mnist_replica.py:159-162,186-190); everyone waits for round n
-                if self.is_chief:
-                    count = self.n_workers if replicas_to_aggregate is None \
-                        else max(1, min(int(replicas_to_aggregate), self.n_workers))
-                    endpoint.call(self.ps_addrs[spec.task], 'apply', key=spec.key, mode=mode,
-                                  first_slot=0, count=count, wait_seq=self.push_seq)
-                self.applied[spec.key] = self.push_seq
-                step = self.step_base + self.push_seq       # one global step per round
-        self.pull()
-        return step
+                wk.clients[spec.key].wait_applied(self.push_seq, self.stream)
+        self._enqueue_pull()
+        self._step_client.read_step_async(self._step_host.data_ptr(), self.stream)
+        self._step_event = torch.cuda.Event()
+        self._step_event.record(self.stream)
+        cur.wait_stream(self.stream)            # the next forward reads the pulled parameters
+        if fetch_step:
+            return self._known_step()
+        return self._last_step
 
     def global_step(self):
         st = endpoint.call(self.ps_addrs[0], 'state', key=(0, 0))
@@ -230,7 +266,8 @@ class ParameterClient(object):
 
     def restore(self, path):
         files = [endpoint.call(a, 'restore', path=path) for a in self.ps_addrs]
-        self.step_base = self.global_step() - self.push_seq
+        self._step_event = None
+        self._last_step = self.global_step()
         self.pull()
         return files
 
