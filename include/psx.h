@@ -310,6 +310,25 @@ int psx_wait_tokens(uint64_t client_id, uint32_t target, void *stream);
  * mnist_replica.py:204) -- no host synchronisation. */
 int psx_read_step_async(uint64_t client_id, int64_t *host_pinned, void *stream);
 
+/* ------------------------------------------- index-list (sparse) rows --- */
+
+/* IndexedSlices push for embedding-like variables (what TF sends
+ * for gather-based models instead of the dense gradient -- the reference's NMF
+ * touches only row blocks of W, examples/matrix_factorization.py:21-28,43-49).
+ * The shard is viewed as a [nelem / row_len, row_len] matrix.  psx_push_rows
+ * copies k rows (rows_dev, k x row_len, src_dtype) and their row indices
+ * (idx_dev, int64, STRICTLY ASCENDING -- the worker de-duplicates its own slices)
+ * into this worker's landing slot and publishes `seq` like psx_push.
+ * psx_apply_rows waits for the slots like psx_apply, merges rows pushed by
+ * several workers in worker order (binary search, no float atomics: bit-
+ * reproducible), divides by `count` for SYNC_MEAN, and applies SGD / Adam ONCE to
+ * every touched row -- untouched rows keep var, m and v; beta powers and
+ * global_step advance once per call. */
+int psx_push_rows(uint64_t client_id, const int64_t *idx_dev, const void *rows_dev, uint64_t k,
+                  uint64_t row_len, int src_dtype, uint32_t seq, void *stream);
+int psx_apply_rows(uint64_t shard_id, int mode, int first_slot, int count, uint64_t row_len,
+                   uint32_t wait_seq, void *stream);
+
 /* Multi-process form (the product runs one process per GPU): one MEMBER per
  * (process, GPU).  The creator makes the multicast object for `n_devices`
  * members and gets its POSIX file descriptor, which the host ships to the other

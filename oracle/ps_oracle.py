@@ -112,6 +112,43 @@ class Shard:
         self._apply(acc)
 
 
+def rows_round(shard, row_len, idx_lists, row_lists, mode):
+    """Index-list (IndexedSlices) round on a :class:`Shard` viewed as
+    [n / row_len, row_len] (reference: the NMF row blocks of
+    examples/matrix_factorization.py:21-28,43-49).  idx_lists[w]: strictly
+    ascending row indices of worker w; row_lists[w]: [k_w, row_len] gradients.
+    A row pushed by several workers gets ((g_w + g_w') + ...) in worker order;
+    SYNC_MEAN divides by the number of workers; SGD / Adam are applied ONCE to
+    every touched row, untouched rows keep var / m / v; beta powers and
+    global_step advance once."""
+    assert mode in (SUM, SYNC_MEAN)
+    W = len(idx_lists)
+    var = shard.var.reshape(-1, row_len)
+    m = shard.m.reshape(-1, row_len)
+    v = shard.v.reshape(-1, row_len)
+    acc = {}
+    for w in range(W):
+        idx = np.asarray(idx_lists[w], np.int64)
+        assert np.all(np.diff(idx) > 0), "indices must be strictly ascending"
+        for k, r in enumerate(idx):
+            g = np.asarray(row_lists[w][k], F)
+            acc[int(r)] = g.copy() if int(r) not in acc else (acc[int(r)] + g).astype(F)
+    alpha = adam_alpha(shard.lr, shard.b1p, shard.b2p) if shard.opt == ADAM else None
+    for r, g in acc.items():
+        if mode == SYNC_MEAN:
+            g = (g / F(W)).astype(F)
+        if shard.opt == SGD:
+            var[r] -= g * shard.lr
+        else:
+            m[r] += (g - m[r]) * (F(1) - shard.b1)
+            v[r] += (g * g - v[r]) * (F(1) - shard.b2)
+            var[r] -= (m[r] * alpha) / (np.sqrt(v[r], dtype=F) + shard.eps)
+    if shard.opt == ADAM:
+        shard.b1p = F(shard.b1p * shard.b1)
+        shard.b2p = F(shard.b2p * shard.b2)
+    shard.step += 1
+
+
 # --------------------------------------------------------------------------
 # bf16 wire format
 # --------------------------------------------------------------------------

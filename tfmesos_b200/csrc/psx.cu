@@ -1320,6 +1320,69 @@ int psx_read_step_async(uint64_t client_id, int64_t *host_pinned, void *stream)
     return PSX_OK;
 }
 
+// ------------------------------------------------ index-list (sparse) rows --
+int psx_push_rows(uint64_t client_id, const int64_t *idx_dev, const void *rows_dev, uint64_t k,
+                  uint64_t row_len, int src_dtype, uint32_t seq, void *stream)
+{
+    Client *c = find(g_clients, client_id);
+    if (!c) return fail(PSX_EINVAL, "unknown client id");
+    if (c->lay.n_slots == 0) return fail(PSX_ESTATE, "shard was created without gradient slots");
+    if (!seq) return fail(PSX_EINVAL, "a row push publishes: seq must be non-zero");
+    if (row_len == 0 || c->lay.nelem % row_len) return fail(PSX_EINVAL, "row_len %llu does not divide the shard's %llu elements", (unsigned long long)row_len, (unsigned long long)c->lay.nelem);
+    if (k && (!idx_dev || !rows_dev)) return fail(PSX_EINVAL, "null index / row pointer");
+    const size_t need = rows_data_off(k) + k * row_len * c->lay.wire_bytes();
+    if (need > c->lay.nelem_pad * c->lay.wire_bytes())
+        return fail(PSX_EINVAL, "%llu rows of %llu do not fit the landing slot (%zu > %zu bytes)", (unsigned long long)k, (unsigned long long)row_len, need, (size_t)(c->lay.nelem_pad * c->lay.wire_bytes()));
+    PSX_DEVICE(c->device);
+    const int grid = grid_for(k * row_len ? k * row_len : 1, kCopyThreads, c->sm_count, 8);
+    unsigned int *flag = &c->hdr()->slot_seq[c->slot];
+    unsigned int *arr = &c->hdr()->arrivals;
+    cudaStream_t st = (cudaStream_t)stream;
+#define PSX_PR(S, D) k_push_rows<S, D><<<grid, kCopyThreads, 0, st>>>(c->my_slot(), (const long long *)idx_dev, (const S *)rows_dev, (size_t)k, (size_t)row_len, &c->block->ticket, flag, arr, seq)
+    const int dt = c->lay.wire;
+    if (src_dtype == PSX_F32 && dt == PSX_F32) PSX_PR(float, float);
+    else if (src_dtype == PSX_F32 && dt == PSX_BF16) PSX_PR(float, __nv_bfloat16);
+    else if (src_dtype == PSX_BF16 && dt == PSX_F32) PSX_PR(__nv_bfloat16, float);
+    else if (src_dtype == PSX_BF16 && dt == PSX_BF16) PSX_PR(__nv_bfloat16, __nv_bfloat16);
+    else return fail(PSX_EINVAL, "unknown dtype %d", src_dtype);
+#undef PSX_PR
+    LAUNCH_CHECK();
+    return PSX_OK;
+}
+
+int psx_apply_rows(uint64_t id, int mode, int first_slot, int count, uint64_t row_len,
+                   uint32_t wait_seq, void *stream)
+{
+    Shard *s = find(g_shards, id);
+    if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    int rc = check_range(first_slot, count, s->lay.n_slots);
+    if (rc) return rc;
+    if (row_len == 0 || s->lay.nelem % row_len) return fail(PSX_EINVAL, "row_len does not divide the shard");
+    if (mode != PSX_MODE_SUM && mode != PSX_MODE_SYNC_MEAN)
+        return fail(PSX_EINVAL, "row applies aggregate (SUM / SYNC_MEAN); apply slots one by one for async");
+    PSX_DEVICE(s->device);
+    rc = wait_slots(s, first_slot, count, wait_seq, stream);
+    if (rc) return rc;
+    PeerSet peers;
+    memset(&peers, 0, sizeof(peers));
+    fill_mirrors(s, &peers);
+    const size_t stride = (size_t)s->lay.nelem_pad * s->lay.wire_bytes();
+    const size_t n_rows = s->lay.nelem / row_len;
+    const int grid = s->sm_count * 4;
+    cudaStream_t st = (cudaStream_t)stream;
+#define PSX_AR(O, M, W) k_apply_rows<O, M, W><<<grid, 256, 0, st>>>(s->hdr(), s->var(), s->m(), s->v(), s->slot(0), stride, first_slot, count, (size_t)row_len, n_rows, peers)
+#define PSX_AR2(O, M) do { if (s->lay.wire == PSX_F32) PSX_AR(O, M, float); else PSX_AR(O, M, __nv_bfloat16); } while (0)
+    const int opt = s->lay.opt;
+    if (opt == PSX_OPT_SGD && mode == PSX_MODE_SUM) PSX_AR2(PSX_OPT_SGD, PSX_MODE_SUM);
+    else if (opt == PSX_OPT_SGD) PSX_AR2(PSX_OPT_SGD, PSX_MODE_SYNC_MEAN);
+    else if (mode == PSX_MODE_SUM) PSX_AR2(PSX_OPT_ADAM, PSX_MODE_SUM);
+    else PSX_AR2(PSX_OPT_ADAM, PSX_MODE_SYNC_MEAN);
+#undef PSX_AR2
+#undef PSX_AR
+    LAUNCH_CHECK();
+    return PSX_OK;
+}
+
 // ----------------------------------------------------------- tensor lists ---
 int psx_list_create(uint64_t client_id, const void *const *dev_ptrs, const uint64_t *offs,
                     const uint64_t *n, int count, uint64_t *out_list_id)

@@ -970,4 +970,130 @@ k_round_mc(ShardHeader *__restrict__ h, float4 *__restrict__ var, float4 *__rest
     finish_apply<OPT, true>(h, peers, 1, 1, b1, b2);
 }
 
+// ---------------------------------------------- index-list (sparse) rows ----
+// IndexedSlices push for embedding-like variables: a worker ships
+// K rows of length D plus their row indices instead of the dense gradient.  The
+// rows land in the worker's OWN landing slot, which is laid out for this as
+//     [ count u64 | pad | idx i64[K] | pad to 16 B | rows wire[K x D] ]
+// Indices must be strictly ascending (unique): the worker de-duplicates its own
+// slices (TF does the same before a sparse Adam apply); duplicates ACROSS workers
+// are merged on the PS in worker order, found by binary search -- no sort, no
+// atomics on floats, bit-reproducible.
+struct RowsHeader {
+    unsigned long long count;
+    unsigned long long row_len;
+};
+__host__ __device__ inline size_t rows_idx_off() { return 16; }
+__host__ __device__ inline size_t rows_data_off(size_t k) { return (16 + k * 8 + 15) / 16 * 16; }
+
+template <typename SRC, typename DST>
+__global__ void __launch_bounds__(kCopyThreads)
+k_push_rows(char *slot, const long long *__restrict__ idx, const SRC *__restrict__ rows, size_t k,
+            size_t d, unsigned int *ticket, unsigned int *flag, unsigned int *arrivals,
+            unsigned int seq)
+{
+    long long *didx = (long long *)(slot + rows_idx_off());
+    DST *drows = (DST *)(slot + rows_data_off(k));
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = tid; i < k; i += nth) didx[i] = idx[i];
+    for (size_t i = tid; i < k * d; i += nth) drows[i] = from_f32<DST>(to_f32<SRC>(rows[i]));
+    if (tid == 0) {
+        RowsHeader *rh = (RowsHeader *)slot;
+        rh->count = k;
+        rh->row_len = d;
+    }
+    if (last_cta(ticket) && threadIdx.x == 0) {
+        *ticket = 0;
+        __threadfence_system();
+        publish_store(flag, seq);
+        publish_add_release(arrivals, 1u);
+    }
+}
+
+__device__ __forceinline__ long long rows_find(const long long *idx, long long n, long long key)
+{
+    long long lo = 0, hi = n;
+    while (lo < hi) {
+        long long mid = (lo + hi) >> 1;
+        if (idx[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < n && idx[lo] == key) ? lo : -1;
+}
+
+// One warp per pushed entry (slot w, position k).  The entry whose worker is the
+// LOWEST one holding that row index is the row's representative: it sums the
+// row's contributions in worker order ((g_w + g_w') + ...), divides for MEAN, and
+// applies SGD / Adam to that row of var (m, v) only -- untouched rows keep their
+// value and their moments ("lazy" sparse semantics).
+template <int OPT, int MODE, typename WIRE>
+__global__ void __launch_bounds__(256)
+k_apply_rows(ShardHeader *__restrict__ h, float *__restrict__ var, float *__restrict__ mom,
+             float *__restrict__ vel, const char *slots, size_t slot_stride, int first, int count,
+             size_t d, size_t n_rows, PeerSet peers)
+{
+    const float lr = h->lr, b1 = h->b1, b2 = h->b2, eps = h->eps;
+    const float omb1 = __fsub_rn(1.0f, b1), omb2 = __fsub_rn(1.0f, b2);
+    const float alpha = (OPT == PSX_OPT_ADAM) ? adam_alpha(lr, h->b1p, h->b2p) : 0.f;
+    const float fcount = (float)count;
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    // entries are numbered slot-major: prefix over the slots' counts
+    size_t total = 0;
+    for (int s = 0; s < count; ++s)
+        total += ((const RowsHeader *)(slots + (size_t)(first + s) * slot_stride))->count;
+    for (size_t e = warp; e < total; e += n_warps) {
+        int w = 0;
+        size_t k = e;
+        for (;; ++w) {
+            const size_t c = ((const RowsHeader *)(slots + (size_t)(first + w) * slot_stride))->count;
+            if (k < c) break;
+            k -= c;
+        }
+        const char *sw = slots + (size_t)(first + w) * slot_stride;
+        const size_t kw = ((const RowsHeader *)sw)->count;
+        const long long row = ((const long long *)(sw + rows_idx_off()))[k];
+        if (row < 0 || (size_t)row >= n_rows) continue;          // out of range: ignored
+        bool rep = true;                                          // lowest worker holding `row`?
+        for (int w2 = 0; w2 < w && rep; ++w2) {
+            const char *s2 = slots + (size_t)(first + w2) * slot_stride;
+            if (rows_find((const long long *)(s2 + rows_idx_off()),
+                          (long long)((const RowsHeader *)s2)->count, row) >= 0)
+                rep = false;
+        }
+        if (!rep) continue;
+        long long pos[PSX_MAX_SLOTS];
+        for (int w2 = w + 1; w2 < count; ++w2) {
+            const char *s2 = slots + (size_t)(first + w2) * slot_stride;
+            pos[w2] = rows_find((const long long *)(s2 + rows_idx_off()),
+                                (long long)((const RowsHeader *)s2)->count, row);
+        }
+        const WIRE *g0 = (const WIRE *)(sw + rows_data_off(kw)) + k * d;
+        for (size_t j = lane; j < d; j += 32) {
+            float g = to_f32<WIRE>(g0[j]);
+            for (int w2 = w + 1; w2 < count; ++w2) {
+                if (pos[w2] < 0) continue;
+                const char *s2 = slots + (size_t)(first + w2) * slot_stride;
+                const size_t k2 = ((const RowsHeader *)s2)->count;
+                g = __fadd_rn(g, to_f32<WIRE>(((const WIRE *)(s2 + rows_data_off(k2)))[(size_t)pos[w2] * d + j]));
+            }
+            if (MODE == PSX_MODE_SYNC_MEAN) g = __fdiv_rn(g, fcount);
+            const size_t at = (size_t)row * d + j;
+            float x = var[at];
+            if (OPT == PSX_OPT_SGD) {
+                x = sgd1(x, g, lr);
+            } else {
+                float m = mom[at], v = vel[at];
+                adam1(x, m, v, g, alpha, omb1, omb2, eps);
+                mom[at] = m;
+                vel[at] = v;
+            }
+            var[at] = x;
+        }
+    }
+    finish_apply<OPT, false>(h, peers, 1, 1, b1, b2);
+}
+
 }  // namespace psx

@@ -580,7 +580,7 @@ class TorchrunCluster(object):
         self.seq = 0
         self._batches = {}
         self.staging = None
-        self.h2d_stream = self.d2h_stream = None
+        self.h2d_stream = self.d2h_stream = self.pull_stream = None
         self.barrier()
 
     def _bcast(self, obj):
@@ -713,9 +713,20 @@ class TorchrunCluster(object):
     def round_host(self, mode):
         """The same round from HOST buffers, software-pipelined over the shards:
         while shard i's gradients cross PCIe (H2D stream), shard i-1 is pushed /
-        applied / pulled (worker + PS streams) and shard i-2's parameters go back
-        to the host (D2H stream).  Both PCIe directions stay busy; with S shards
-        per bucket the step costs about (S+1)/S of one direction's transfer."""
+        applied / pulled and shard i-2's parameters go back to the host (D2H
+        stream).  Five streams, so that no stage waits behind another stage's
+        dependency: H2D, push, apply (PS), pull, D2H -- with pushes and pulls on
+        ONE stream, pull(i) sat behind push(i+1), i.e. behind H2D(i+1), and the
+        pipeline was one stage deeper than necessary (measured 18.5 ms = 18/16 of
+        the PCIe duplex floor; (S+1)/S is the design point).
+        Shards hosted by this rank skip the staging hop altogether: their gradients
+        are DMA'd straight into this worker's landing slot and their parameters
+        straight out of ``var`` (f32 wire).
+        Every rank walks the shards in the SAME order: a shard's apply needs all W
+        pushes, so it can only complete (and its pull / D2H start) when the slowest
+        rank has reached it -- identical order makes that as early as possible, and
+        the pushes are PCIe-paced (49 GB/s per rank), far below what incast into one
+        NVLink port would need to matter."""
         import torch
         assert self.worker is not None and not self.fused, \
             "round_host runs on worker ranks of a staged-path cluster"
@@ -724,40 +735,68 @@ class TorchrunCluster(object):
         if self.h2d_stream is None:
             self.h2d_stream = torch.cuda.Stream(device=self.device)
             self.d2h_stream = torch.cuda.Stream(device=self.device)
+            self.pull_stream = torch.cuda.Stream(device=self.device)
+            # direct DMA targets of the shards hosted here (f32 wire only: a bf16 slot
+            # or parameter needs the casting kernels)
+            self._direct = {}
+            if self.worker.wire == psx.F32:
+                for key, ps in self.servers.items():
+                    n = ps.spec.nelem
+                    self._direct[key] = (
+                        psx.device_tensor(ps.shard.ptr(psx.SLOT0 + self.worker.index), n,
+                                          torch.float32, self.device),
+                        psx.device_tensor(ps.shard.ptr(psx.VAR), n, torch.float32, self.device))
         st, wk = self.staging, self.worker
-        ws, pss, hs, ds = self.worker_stream, self.ps_stream, self.h2d_stream, self.d2h_stream
+        ws, pss, hs, ds, pl = (self.worker_stream, self.ps_stream, self.h2d_stream,
+                               self.d2h_stream, self.pull_stream)
         self.seq += 1
         seq = self.seq
         hs.wait_stream(ws)                 # last round's pushes have read grad_flat
+        hs.wait_stream(pss)                # ... and last round's applies their landing slots
         self.mailbox.consume(self.n_shards, ws)   # counted rendez-vous: start from zero
-        # same shard order on every rank here: shard i's pull sits behind shard
-        # i+1's push on one stream, so a per-rank rotation would make the ranks
-        # wait on each other in a cycle (and PCIe, not NVLink incast, is the limit)
+        pl.wait_stream(ds)                 # last round's D2H has read param_flat
         shards = self.topo.shards
-        for i in range(len(shards) + 1):
-            if i < len(shards):
-                sp = shards[i]
-                g = wk.grad_flat[sp.task][sp.off:sp.off + sp.nelem]
-                with torch.cuda.stream(hs):
-                    g.copy_(st.grad[sp.task][sp.off:sp.off + sp.nelem], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(hs)
-                ws.wait_event(ev)
-                wk.clients[sp.key].push(g.data_ptr(), sp.nelem, 0, wk.wire, seq, ws)
-                ps = self.servers.get(sp.key)
-                if ps is not None:
-                    ps.shard.apply_counted(mode, 0, self.n_workers, pss)
-            if i >= 1:
-                sp = shards[i - 1]
-                p = wk.param_flat[sp.task][sp.off:sp.off + sp.nelem]
-                wk.clients[sp.key].pull(p.data_ptr(), sp.nelem, 0, wk.wire, seq, ws)
+        for sp in shards:
+            host_g = st.grad[sp.task][sp.off:sp.off + sp.nelem]
+            host_p = st.param[sp.task][sp.off:sp.off + sp.nelem]
+            direct = self._direct.get(sp.key)
+            # ---- gradients in
+            with torch.cuda.stream(hs):
+                if direct is not None:
+                    direct[0].copy_(host_g, non_blocking=True)
+                else:
+                    g = wk.grad_flat[sp.task][sp.off:sp.off + sp.nelem]
+                    g.copy_(host_g, non_blocking=True)
                 ev = torch.cuda.Event()
-                ev.record(ws)
-                ds.wait_event(ev)
+                ev.record(hs)
+            ws.wait_event(ev)
+            if direct is not None:         # already in the slot: publish flag + arrival only
+                wk.clients[sp.key].signal(seq, ws)
+            else:
+                wk.clients[sp.key].push(g.data_ptr(), sp.nelem, 0, wk.wire, seq, ws)
+            # ---- apply (owner only)
+            ps = self.servers.get(sp.key)
+            if ps is not None:
+                ps.shard.apply_counted(mode, 0, self.n_workers, pss)
+            # ---- parameters out
+            if direct is not None:
+                wk.clients[sp.key].wait_applied(seq, pl)
+                ev2 = torch.cuda.Event()
+                ev2.record(pl)
+                ds.wait_event(ev2)
                 with torch.cuda.stream(ds):
-                    st.param[sp.task][sp.off:sp.off + sp.nelem].copy_(p, non_blocking=True)
+                    host_p.copy_(direct[1], non_blocking=True)
+            else:
+                p = wk.param_flat[sp.task][sp.off:sp.off + sp.nelem]
+                wk.clients[sp.key].pull(p.data_ptr(), sp.nelem, 0, wk.wire, seq, pl)
+                ev2 = torch.cuda.Event()
+                ev2.record(pl)
+                ds.wait_event(ev2)
+                with torch.cuda.stream(ds):
+                    host_p.copy_(p, non_blocking=True)
         self.mailbox.wait(self.n_shards, ws)   # every shard applied (invariant restored)
         ws.wait_stream(ds)                 # the step ends when the host has the parameters
+        ws.wait_stream(pl)
 
     def close(self):
         self.barrier()

@@ -110,6 +110,8 @@ SIGNATURES = {
     "psx_push_stamped": (_i32, [_u64, _vp, _u64, _u64, _i32, _u32, _u32, _vp]),
     "psx_wait_tokens": (_i32, [_u64, _u32, _vp]),
     "psx_read_step_async": (_i32, [_u64, _vp, _vp]),
+    "psx_push_rows": (_i32, [_u64, _vp, _vp, _u64, _u64, _i32, _u32, _vp]),
+    "psx_apply_rows": (_i32, [_u64, _i32, _i32, _i32, _u64, _u32, _vp]),
     "psx_batch": (_i32, [ctypes.POINTER(Op), _i32, ctypes.POINTER(_i32)]),
     "psx_launch_count": (_u64, []),
     "psx_shard_ptr": (_i32, [_u64, _i32, ctypes.POINTER(_vp)]),
@@ -239,6 +241,10 @@ class Shard(object):
     def register_client(self, slot, client_handle):
         _check(lib().psx_shard_register_client(self.id, int(slot), client_handle))
 
+    def apply_rows(self, mode, first_slot, count, row_len, wait_seq=0, stream=None):
+        _check(lib().psx_apply_rows(self.id, int(mode), int(first_slot), int(count),
+                                    int(row_len), int(wait_seq), _stream_ptr(stream)))
+
     def serve_start(self, mode, replicas_to_aggregate=1, depth=8):
         """Request-free serving loop on this shard (psx_serve_start)."""
         _check(lib().psx_serve_start(self.id, int(mode), int(replicas_to_aggregate), int(depth)))
@@ -324,6 +330,12 @@ class Client(object):
     def pull(self, param_ptr, n, off=0, dtype=F32, wait_seq=0, stream=None):
         _check(lib().psx_pull(self.id, param_ptr, int(off), int(n), int(dtype),
                               int(wait_seq), _stream_ptr(stream)))
+
+    def push_rows(self, idx_ptr, rows_ptr, k, row_len, dtype=F32, seq=1, stream=None):
+        """IndexedSlices push: k rows (k x row_len at rows_ptr) with strictly ascending
+        int64 row indices at idx_ptr."""
+        _check(lib().psx_push_rows(self.id, idx_ptr, rows_ptr, int(k), int(row_len), int(dtype),
+                                   int(seq), _stream_ptr(stream)))
 
     def push_stamped(self, grad_ptr, n, off=0, dtype=F32, seq=1, stamp=0, stream=None):
         _check(lib().psx_push_stamped(self.id, grad_ptr, int(off), int(n), int(dtype), int(seq),

@@ -80,7 +80,75 @@ def main():
     }
     out["note"] = ("GB/s per direction per GPU; local_copy counts bytes once (read+write "
                    "= 2x that); mixed_bidir carries 2 GiB per direction")
+    G = torch.cuda.device_count()
+    if G >= 4:
+        out.update(many_gpu(G))
     print(json.dumps(out))
+
+
+def many_gpu(G):
+    """W -> 1 incast (W GPUs store into GPU 0 / GPU 0's kernel loads from W GPUs) and
+    the all-pairs pattern of the striped round (every GPU loads 1/G from every other
+    GPU and stores 1/G into every other GPU), G = all visible GPUs."""
+    for a in range(G):
+        for b_ in range(G):
+            if a != b_:
+                psx.enable_peer(a, b_)
+    src = [torch.zeros(N, dtype=torch.uint8, device="cuda:%d" % d) for d in range(G)]
+    dst = [torch.zeros(N, dtype=torch.uint8, device="cuda:%d" % d) for d in range(G)]
+    land = [torch.zeros(N, dtype=torch.uint8, device="cuda:0") for _ in range(min(G - 1, 7))]
+    st = [[torch.cuda.Stream(device=d) for _ in range(G)] for d in range(G)]
+
+    def run(ops, used):
+        times = []
+        for it in range(9):
+            for d in range(G):
+                torch.cuda.synchronize(d)
+            ev = {}
+            for d in used:
+                with torch.cuda.device(d):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(st[d][0])
+                    for k in range(1, G):
+                        st[d][k].wait_stream(st[d][0])
+                    ev[d] = (e0, e1)
+            for dev, dptr, sptr, nbytes, k in ops:
+                psx.copy(dev, dptr, sptr, nbytes, st[dev][k])
+            for d in used:
+                with torch.cuda.device(d):
+                    for k in range(1, G):
+                        st[d][0].wait_stream(st[d][k])
+                    ev[d][1].record(st[d][0])
+            for d in range(G):
+                torch.cuda.synchronize(d)
+            if it >= 3:
+                times.append(max(ev[d][0].elapsed_time(ev[d][1]) for d in used))
+        times.sort()
+        return times[len(times) // 2]
+
+    out = {"gpus": G}
+    for W in [w for w in (1, 2, 4, 7) if w < G]:
+        # W workers each STORE 1 GiB into GPU 0 (push incast)
+        ops = [(w, land[w - 1].data_ptr(), src[w].data_ptr(), N, 0) for w in range(1, W + 1)]
+        ms = run(ops, list(range(1, W + 1)))
+        out["incast_write_%dto1" % W] = {"ms": ms, "ingress_GBps_at_gpu0": W * N / ms / 1e6}
+        # GPU 0 LOADS 1 GiB from each of W workers (PS-side gather), one stream per source
+        ops = [(0, land[w - 1].data_ptr(), src[w].data_ptr(), N, w) for w in range(1, W + 1)]
+        ms = run(ops, [0])
+        out["gather_read_1from%d" % W] = {"ms": ms, "ingress_GBps_at_gpu0": W * N / ms / 1e6}
+    part = N // G // 16 * 16
+    ops = []
+    for a in range(G):
+        for k, b_ in enumerate([x for x in range(G) if x != a]):
+            ops.append((a, dst[a].data_ptr() + b_ * part, src[b_].data_ptr() + a * part, part, k))
+            ops.append((a, dst[b_].data_ptr() + a * part, src[a].data_ptr() + b_ * part, part,
+                        (k + 1) % (G - 1) + 0))
+    ms = run(ops, list(range(G)))
+    out["all_pairs_read_plus_write"] = {
+        "ms": ms, "GBps_per_direction_per_gpu": 2 * (G - 1) * part / ms / 1e6,
+        "note": "every GPU loads 1/G GiB from and stores 1/G GiB into every other GPU at once "
+                "(the unicast striped round's traffic pattern)"}
+    return out
 
 
 if __name__ == "__main__":

@@ -12,6 +12,7 @@
 #   launches     ncu launch list of the default bench command (1 GPU)
 #   ncufull:K    ncu --set full of kernel regex K in the default bench command (1 GPU)
 #   sass         cuobjdump -sass extracts (UBLKCP in k_list_tma, multimem in k_round_mc)
+#   pcie         tools/bench_pcie.py on all N GPUs at once (the e2e ceiling)
 #   p2p          tools/bench_p2p.py (NVLink peaks: uni, duplex, incast, all pairs)
 #   nvls         tools/bench_nvls.py (single-process NVLS primitives)
 #   sweep:ARGS   tools/bench_sweep.py under torchrun (world = N) with extra args
@@ -72,6 +73,13 @@ for stage in "$@"; do
       grep -c UBLKCP $OUT/libpsx.sass | sed 's/^/UBLKCP lines: /' | tee -a $OUT/summary.txt ;;
     p2p)
       timeout 900 python tools/bench_p2p.py > $OUT/p2p_n$N.json 2> $OUT/p2p_n$N.err; say "p2p rc=$?"; cut -c1-3000 $OUT/p2p_n$N.json; tail -3 $OUT/p2p_n$N.err ;;
+    pcie)
+      if [ $N -gt 1 ]; then
+        timeout 600 bash -c "$(declare -f trun); PORT=29480; trun $N tools/bench_pcie.py" > $OUT/pcie_n$N.json 2> $OUT/pcie_n$N.err; say "pcie rc=$?"
+      else
+        timeout 600 python tools/bench_pcie.py > $OUT/pcie_n$N.json 2> $OUT/pcie_n$N.err; say "pcie rc=$?"
+      fi
+      cat $OUT/pcie_n$N.json; tail -3 $OUT/pcie_n$N.err ;;
     nvls)
       timeout 600 python tools/bench_nvls.py > $OUT/nvls_n$N.json 2> $OUT/nvls_n$N.err; say "nvls rc=$?"; cat $OUT/nvls_n$N.json; tail -3 $OUT/nvls_n$N.err ;;
     sweep)
