@@ -579,7 +579,18 @@ def run_b200(args):
         torch.cuda.synchronize()
         return cl_
 
-    cl = make_cluster(path, args.stripes)
+    nvls_note = None
+    try:
+        cl = make_cluster(path, args.stripes)
+    except engine.NvlsUnavailable as exc:
+        if args.path == "nvls":
+            raise
+        # `auto` picked the switch path from the device attribute, but building the
+        # multicast team failed (on every rank alike): run the unicast kernel instead.
+        # Decided here, once, at set-up -- never per call.
+        nvls_note = "NVLS set-up failed, unicast round used: %s" % str(exc)[:200]
+        path = "fused"
+        cl = make_cluster(path, args.stripes)
     W = cl.n_workers
 
     # L2 flush buffer for workloads smaller than L2
@@ -815,7 +826,7 @@ def run_b200(args):
             "dtype": "f32" if args.wire == "f32" else "f32 master / bf16 wire",
             "data": "synthetic",
             "config": cfg,
-            "path_resolved": path, "n_workers": W, "stripes_per_bucket": resolved_stripes,
+            "path_resolved": path, "path_note": nvls_note, "n_workers": W, "stripes_per_bucket": resolved_stripes,
             "verified": verified["ok"] if verified else None,
             "verification": verified,
             "steps_per_sec": 1e3 / ms_step * (W if args.mode == "async" else 1),

@@ -277,9 +277,12 @@ int psx_mc_reduce(uint64_t id, int member, void *dst_dev, uint64_t off_bytes, ui
 /* The reference's DEFAULT discipline -- every worker's push applied when it
  * arrives, nobody waits for anybody (examples/mnist/mnist_replica.py:198-205,
  * examples/mnist/mnist.py:63-72) -- without a host request per step.
- * psx_serve_start gives the shard a serving loop: one host thread keeps `depth`
- * iterations of  [stream-wait arrivals >= 1] [k_pick] [k_apply over the picked
- * slots]  enqueued ahead on the shard's own stream.
+ * psx_serve_start gives the shard a serving loop: one host thread polls the
+ * shard's arrival counter (a 4-byte copy on the shard's own stream) and launches
+ * [k_pick] [k_apply over the picked slots] whenever pushes have arrived; after 64
+ * empty polls in a row it sleeps idle_sleep_us between polls (0 = keep spinning).
+ * (No stream is ever left blocked in a wait-value for work that has not been
+ * submitted yet: streams of a process share a few hardware channels.)
  *   mode PSX_MODE_ASYNC_ORDERED: every unconsumed push found by a pick is applied
  *     on its own (own beta powers, one global_step each), picks in arrival order,
  *     slots of one pick in slot order; the worker's client block receives the
@@ -293,7 +296,7 @@ int psx_mc_reduce(uint64_t id, int member, void *dst_dev, uint64_t off_bytes, ui
  *     fast or slow, like the chief's token queue.
  * The host accessors (*_values, *_state, set_hyper, (un)register) pause the loop
  * for their duration; psx_shard_destroy stops it. */
-int psx_serve_start(uint64_t shard_id, int mode, int replicas_to_aggregate, int depth);
+int psx_serve_start(uint64_t shard_id, int mode, int replicas_to_aggregate, int idle_sleep_us);
 int psx_serve_stop(uint64_t shard_id);
 int psx_serve_stats(uint64_t shard_id, uint64_t *iterations, uint32_t *served, uint32_t *dropped,
                     int64_t *step);

@@ -25,7 +25,7 @@ def _free_port():
     return port
 
 
-def _launch(world, cases, rounds=3, timeout=1500, only=None):
+def _launch(world, cases, rounds=3, timeout=1100, only=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
            "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()),
@@ -47,6 +47,7 @@ def _n_gpus():
     return torch.cuda.device_count()
 
 
+@pytest.mark.timeout(1200)
 def test_world2_small_and_full_size_bit_exact():
     """2 ranks: every path x wire x discipline on the MNIST-replica bucket, and the
     full 2.0e8-element NMF parameter set through the fused round (SCALE's
@@ -56,19 +57,21 @@ def test_world2_small_and_full_size_bit_exact():
     assert "nmf/fused/f32/sum/round" in out and "round_host" in out
 
 
+@pytest.mark.timeout(900)
 def test_world4_small_bit_exact():
     """4 ranks incl. PS shards on ranks that host no worker (dedicated PS GPUs)."""
-    out = _launch(4, "small")
+    out = _launch(4, "small", timeout=850)
     assert "dedicated-ps" in out
 
 
 @pytest.mark.multigpu
+@pytest.mark.timeout(1500)
 def test_one_rank_per_gpu_up_to_8_full_size_and_nvls():
     """One rank per GPU over NVLink (world = min(n_gpus, 8)): small + full-size
     cases bit-exact; the NVLS round bit-exact at world 2, rtol 2e-6 beyond."""
     world = min(_n_gpus(), 8)
     from tfmesos_b200 import psx
-    cases = "small,full"
+    cases = "small,fullmin"
     if all(psx.nvls_supported(d) for d in range(world)):
         cases += ",nvls"
-    _launch(world, cases, timeout=3000)
+    _launch(world, cases, timeout=1400)

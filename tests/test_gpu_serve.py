@@ -102,7 +102,7 @@ def test_served_async_concurrent_pushes_are_all_consumed():
     W, R = 4, 6
     rig = _Rig(W, psx.OPT_SGD, 0.05)
     try:
-        rig.shard.serve_start(psx.MODE_ASYNC_ORDERED, depth=4)
+        rig.shard.serve_start(psx.MODE_ASYNC_ORDERED, idle_sleep_us=50)
         total = np.zeros(N, np.float64)
         steps = [[] for _ in range(W)]
         for r in range(1, R + 1):

@@ -413,15 +413,26 @@ int launch_round_mc(Shard *s, int mode, const PeerSet &peers, cudaStream_t st, c
 }
 
 // ------------------------------------------------- request-free serving ----
-// One host thread per served shard keeps `depth` iterations of
-//   cuStreamWaitValue32(arrivals >= 1) ; k_pick ; k_apply<.., PickSrc>
-// enqueued ahead on the shard's own (non-blocking) stream; it sleeps in
-// cudaEventSynchronize (blocking-sync events) while the GPU waits for pushes.
+// One host thread per served shard.  It POLLS the shard's arrival counter (a
+// 4-byte device->host copy on the serving stream, ~6 us) and, when pushes have
+// arrived, launches  k_pick ; k_apply<.., PickSrc>  on that stream.
+//
+// Why not pre-enqueued cuStreamWaitValue32(arrivals >= 1) iterations (the first
+// implementation): a stream blocked in a wait-value holds its hardware channel,
+// and CUDA multiplexes all streams of a process onto a few channels
+// (CUDA_DEVICE_MAX_CONNECTIONS, 8 by default).  Work submitted LATER on another
+// stream that aliases to the same channel -- the push that would satisfy the
+// wait when worker and PS share a process, or the accessor / stop path inside the
+// PS process -- queues up BEHIND the wait and never runs: a deadlock that depends
+// on how many streams the process happens to have created (it took a whole test
+// run down, profiles/r23).  Every stream wait this library still issues is
+// submitted after the work it waits for (or waits for another process), so
+// submission order is always a valid execution order.
 struct Server {
     std::thread th;
     std::atomic<bool> stop{false};
     cudaStream_t stream = nullptr;
-    int mode = PSX_MODE_ASYNC_ORDERED, aggregate = 1, depth = 8;
+    int mode = PSX_MODE_ASYNC_ORDERED, aggregate = 1, idle_sleep_us = 0;
     std::atomic<uint64_t> iterations{0};
     std::atomic<int> error{0};
     char errmsg[256] = "";
@@ -429,8 +440,6 @@ struct Server {
 
 int serve_iteration(Shard *s, Server *sv)
 {
-    int rc = stream_wait_geq(sv->stream, &s->hdr()->arrivals, 1u);
-    if (rc) return rc;
     const int n_slots = s->lay.n_slots;
     if (sv->mode == PSX_MODE_ASYNC_ORDERED)
         k_pick<PSX_MODE_ASYNC_ORDERED><<<1, 32, 0, sv->stream>>>(s->hdr(), n_slots, 1);
@@ -451,31 +460,40 @@ int serve_iteration(Shard *s, Server *sv)
 void serve_main(Shard *s, Server *sv)
 {
     cudaSetDevice(s->device);
-    std::vector<cudaEvent_t> ev((size_t)sv->depth);
-    for (auto &e : ev) cudaEventCreateWithFlags(&e, cudaEventBlockingSync | cudaEventDisableTiming);
+    unsigned int *seen = nullptr;                 // pinned landing word of the poll
+    cudaError_t e = cudaHostAlloc((void **)&seen, sizeof(unsigned int), cudaHostAllocDefault);
     uint64_t it = 0;
-    while (!sv->stop.load()) {
-        if (it >= (uint64_t)sv->depth) cudaEventSynchronize(ev[it % sv->depth]);  // iteration it-depth done
-        if (sv->stop.load()) break;
+    int idle = 0;
+    while (e == cudaSuccess && !sv->stop.load()) {
+        // ordered behind the previous iteration's kernels: reads the counter AFTER
+        // that pick took its pushes off
+        e = cudaMemcpyAsync(seen, &s->hdr()->arrivals, sizeof(unsigned int), cudaMemcpyDeviceToHost,
+                            sv->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(sv->stream);
+        if (e != cudaSuccess) break;
+        if ((int)*seen < 1) {                     // signed: a pick may run ahead of a counter bump
+            if (sv->idle_sleep_us > 0 && ++idle > 64) usleep((useconds_t)sv->idle_sleep_us);
+            continue;
+        }
+        idle = 0;
         int rc = serve_iteration(s, sv);
         if (rc) {
-            snprintf(sv->errmsg, sizeof(sv->errmsg), "%s", g_err);
+            snprintf(sv->errmsg, sizeof(sv->errmsg), "%.250s", g_err);
             sv->error.store(rc);
             break;
         }
-        cudaEventRecord(ev[it % sv->depth], sv->stream);
-        ++it;
-        sv->iterations.store(it);
+        sv->iterations.store(++it);
     }
-    cudaError_t e = cudaStreamSynchronize(sv->stream);    // the release kernel lets the queue drain
+    cudaError_t e2 = cudaStreamSynchronize(sv->stream);
+    if (e == cudaSuccess) e = e2;
     if (e != cudaSuccess && sv->error.load() == 0) {
         snprintf(sv->errmsg, sizeof(sv->errmsg), "serving stream: %s", cudaGetErrorString(e));
         sv->error.store(PSX_ECUDA);
     }
-    for (auto &e2 : ev) cudaEventDestroy(e2);
+    if (seen) cudaFreeHost(seen);
 }
 
-int serve_start_impl(Shard *s, int mode, int aggregate, int depth)
+int serve_start_impl(Shard *s, int mode, int aggregate, int idle_sleep_us)
 {
     if (s->server) return fail(PSX_ESTATE, "shard is already being served");
     if (s->lay.n_slots < 1) return fail(PSX_ESTATE, "serving needs landing slots (n_slots >= 1)");
@@ -483,15 +501,12 @@ int serve_start_impl(Shard *s, int mode, int aggregate, int depth)
         return fail(PSX_EINVAL, "serve mode must be ASYNC_ORDERED or SYNC_MEAN");
     if (mode == PSX_MODE_SYNC_MEAN && (aggregate < 1 || aggregate > s->lay.n_slots))
         return fail(PSX_EINVAL, "replicas_to_aggregate %d outside 1..%d", aggregate, s->lay.n_slots);
-    if (depth < 1) depth = 8;
-    if (depth > 64) depth = 64;
-    int rc = resolve_memops();
-    if (rc) return rc;
+    if (idle_sleep_us < 0) idle_sleep_us = 0;
     PSX_DEVICE(s->device);
     Server *sv = new Server();
     sv->mode = mode;
     sv->aggregate = aggregate;
-    sv->depth = depth;
+    sv->idle_sleep_us = idle_sleep_us;
     cudaError_t e = cudaStreamCreateWithFlags(&sv->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete sv;
@@ -502,45 +517,37 @@ int serve_start_impl(Shard *s, int mode, int aggregate, int depth)
     return PSX_OK;
 }
 
-// Stops the loop and leaves the shard quiescent: queued iterations run through
-// without picking (stop flag + released counter), pushes that arrive meanwhile
-// stay flagged and counted for the next psx_serve_start.
-int serve_stop_impl(Shard *s, int *mode, int *aggregate, int *depth)
+// Stops the loop and leaves the shard quiescent (the thread finishes the iteration
+// it is in).  Pushes that arrive while stopped stay flagged and counted for the
+// next psx_serve_start.
+int serve_stop_impl(Shard *s, int *mode, int *aggregate, int *idle_sleep_us)
 {
     Server *sv = s->server;
     if (!sv) return PSX_OK;
-    PSX_DEVICE(s->device);
     sv->stop.store(true);
-    cudaStream_t side = nullptr;
-    CU_TRY(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-    k_serve_release<<<1, 1, 0, side>>>(s->hdr());
-    cudaError_t e = cudaStreamSynchronize(side);
     sv->th.join();
-    if (e == cudaSuccess) {
-        k_serve_reset<<<1, 1, 0, side>>>(s->hdr());
-        e = cudaStreamSynchronize(side);
+    {
+        DeviceGuard g(s->device);
+        cudaStreamDestroy(sv->stream);
     }
-    cudaStreamDestroy(side);
-    cudaStreamDestroy(sv->stream);
     if (mode) *mode = sv->mode;
     if (aggregate) *aggregate = sv->aggregate;
-    if (depth) *depth = sv->depth;
+    if (idle_sleep_us) *idle_sleep_us = sv->idle_sleep_us;
     int err = sv->error.load();
     char msg[256];
     snprintf(msg, sizeof(msg), "%s", sv->errmsg);
     s->server = nullptr;
     delete sv;
     if (err) return fail(err, "serving loop failed: %s", msg);
-    if (e != cudaSuccess) return fail(PSX_ECUDA, "stopping the serving loop: %s", cudaGetErrorString(e));
     return PSX_OK;
 }
 
-// Host accessors drain the device; a served shard always has iterations waiting
-// for pushes, so they pause the loop for their duration instead.
+// Host accessors pause the serving loop for their duration: one consistent view of
+// var / m / v / state, and no apply is launched under a host copy.
 struct ServePause {
     Shard *s;
     bool was = false;
-    int mode = 0, aggregate = 1, depth = 8, rc = PSX_OK;
+    int mode = 0, aggregate = 1, depth = 0, rc = PSX_OK;
     explicit ServePause(Shard *sh) : s(sh)
     {
         if (s->server) {
@@ -1251,11 +1258,11 @@ int psx_wait_applied(uint64_t client_id, uint32_t seq, void *stream)
 }
 
 // ------------------------------------------------ request-free serving ABI --
-int psx_serve_start(uint64_t shard_id, int mode, int replicas_to_aggregate, int depth)
+int psx_serve_start(uint64_t shard_id, int mode, int replicas_to_aggregate, int idle_sleep_us)
 {
     Shard *s = find(g_shards, shard_id);
     if (!s) return fail(PSX_EINVAL, "unknown shard id");
-    return serve_start_impl(s, mode, replicas_to_aggregate, depth);
+    return serve_start_impl(s, mode, replicas_to_aggregate, idle_sleep_us);
 }
 
 int psx_serve_stop(uint64_t shard_id)

@@ -37,7 +37,7 @@ struct ShardHeader {
     unsigned int arrivals;            // +1 per completed push / signal (any slot): lets the
                                       // PS wait for "all W workers of round r" with ONE memop
     // ---- request-free serving (psx_serve_start): the PS consumes pushes as they ARRIVE
-    unsigned int stop;                // set by psx_serve_stop: queued iterations pick nothing
+    unsigned int reserved0;
     unsigned int pick_n;              // slots the current iteration's apply consumes ...
     unsigned int pick[PSX_MAX_SLOTS]; // ... in this order (arrival order between picks)
     unsigned int pick_seq[PSX_MAX_SLOTS];   // push sequence number consumed per picked slot
@@ -532,10 +532,11 @@ __device__ __forceinline__ void finish_apply(ShardHeader *h, const PeerSet &peer
 // ---------------------------------------------------- request-free serving ----
 // The reference's default discipline: every worker's push is applied when it
 // ARRIVES and nobody waits for anybody (examples/mnist/mnist_replica.py:198-205,
-// mnist.py:63-72) -- with no host in the loop.  The PS keeps a few iterations of
-//     cuStreamWaitValue32(arrivals >= 1) ; k_pick ; k_apply<.., PickSrc>
-// enqueued ahead on one stream per shard (psx_serve_start).  A push bumps
-// `arrivals`; the wait releases; k_pick (one warp) looks at every slot flag,
+// mnist.py:63-72) -- with no request from the worker.  Per batch of arrivals the PS runs
+//     k_pick ; k_apply<.., PickSrc>
+// issued by a host thread that polls the counter (psx_serve_start; psx.cu explains
+// why the waits are not pre-enqueued on the stream).  A push bumps
+// `arrivals`; the poll sees it; k_pick (one warp) looks at every slot flag,
 // lists the slots holding an unconsumed push in the header and takes them off the
 // counter; the apply kernel consumes exactly that list in ONE pass (in list order,
 // each with its own beta powers: the serialisable async schedule) and its last CTA
@@ -554,8 +555,7 @@ __global__ void k_pick(ShardHeader *h, int n_slots, int aggregate)
     const int s = threadIdx.x;
     unsigned int seq = 0;
     bool fresh = false;
-    const bool stopping = ld_sys(&h->stop) != 0;
-    if (s < n_slots && !stopping) {
+    if (s < n_slots) {
         seq = ld_sys(&h->slot_seq[s]);
         fresh = seq != h->slot_seen[s];
     }
@@ -589,7 +589,7 @@ __global__ void k_pick(ShardHeader *h, int n_slots, int aggregate)
         }
         unsigned int n_pending = 0;
         for (int k = 0; k < n_slots; ++k) n_pending += h->pending[k];
-        if (!stopping && n_pending >= (unsigned int)aggregate) {
+        if (n_pending >= (unsigned int)aggregate) {
             for (int r = 0; r < aggregate; ++r) {          // the first R by arrival
                 int best = -1;
                 for (int k = 0; k < n_slots; ++k)
@@ -653,20 +653,6 @@ __device__ __forceinline__ void finish_served(ShardHeader *h, int count, float b
             if (cb) publish_add(&cb->tokens, 1u);
         }
     }
-}
-
-// psx_serve_stop: let every queued iteration run through without picking anything
-__global__ void k_serve_release(ShardHeader *h)
-{
-    h->stop = 1u;
-    __threadfence_system();
-    atomicAdd(&h->arrivals, 1u << 30);
-}
-__global__ void k_serve_reset(ShardHeader *h)
-{
-    atomicSub(&h->arrivals, 1u << 30);      // pushes that came in meanwhile stay counted
-    h->stop = 0u;
-    h->pick_n = 0u;
 }
 
 constexpr int kApplyThreads = 256;

@@ -156,7 +156,7 @@ class Endpoint(object):
             self.stream().synchronize()
             shard.round_bind(slot, grad_handle, param_handle, elem_off)
 
-    def do_serve(self, key, mode, replicas_to_aggregate=1, depth=8):
+    def do_serve(self, key, mode, replicas_to_aggregate=1, idle_sleep_us=20):
         """Start the shard's request-free serving loop (psx_serve_start): from now on
         pushes are consumed as they arrive, with no request per step -- the
         reference's default discipline (examples/mnist/mnist_replica.py:198-205) or,
@@ -166,8 +166,8 @@ class Endpoint(object):
             entry = self.shards[key]
             want = (int(mode), int(replicas_to_aggregate))
             if entry[3] is None:
-                entry[0].serve_start(want[0], want[1], depth)
-                entry[3] = want + (int(depth),)
+                entry[0].serve_start(want[0], want[1], idle_sleep_us)
+                entry[3] = want + (int(idle_sleep_us),)
             elif entry[3][:2] != want:
                 raise RuntimeError('shard %r is served with mode/aggregate %r, asked for %r'
                                    % (key, entry[3][:2], want))

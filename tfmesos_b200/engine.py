@@ -418,6 +418,11 @@ def torchrun_topology(layout, world, stripes=None, ps_ranks=None, worker_ranks=N
     return Topology(layout, ps_ranks, list(worker_ranks))
 
 
+class NvlsUnavailable(RuntimeError):
+    """The NVSwitch multicast set-up failed on some rank; raised on EVERY rank, at
+    cluster construction (the path is chosen at init, never per call)."""
+
+
 class McArena(object):
     """This rank's member of one NVSwitch multicast object shared by all worker
     ranks (psx_mcx_*): a VMM allocation in this GPU's HBM that is mapped twice --
@@ -434,8 +439,14 @@ class McArena(object):
         self.device, self.rank, self.world = int(device), int(rank), int(world)
         self.cursor = 0
         fd = -1
+        self.mcx = None
         if rank == 0:
-            self.mcx = psx.McMember.create(device, world, nbytes)
+            try:
+                self.mcx = psx.McMember.create(device, world, nbytes)
+            except RuntimeError:
+                if world > 1:
+                    broadcast(None)        # the others must not wait for a socket name
+                raise
             fd = self.mcx.fd
         if world > 1:
             if rank == 0:
@@ -443,6 +454,7 @@ class McArena(object):
                 srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
                 srv.bind(name)
                 srv.listen(world)
+                srv.settimeout(120)
                 broadcast(name)
                 for _ in range(world - 1):
                     conn, _ = srv.accept()
@@ -452,7 +464,10 @@ class McArena(object):
                 srv.close()
             else:
                 name = broadcast(None)
+                if name is None:
+                    raise RuntimeError("rank 0 could not create the multicast object")
                 c = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                c.settimeout(120)
                 c.connect(name)
                 _, fds, _, _ = socket.recv_fds(c, 16, 1)
                 self.mcx = psx.McMember.import_fd(device, world, nbytes, fds[0])
@@ -475,7 +490,9 @@ class McArena(object):
         return off, psx.device_tensor(self.uc + off, nbytes // esz, dtype, self.device, self)
 
     def destroy(self):
-        self.mcx.destroy()
+        if self.mcx is not None:
+            self.mcx.destroy()
+            self.mcx = None
 
 
 class TorchrunCluster(object):
@@ -532,9 +549,21 @@ class TorchrunCluster(object):
             need = sum(2 * _round_up(_round_up(sum(s.nelem for s in self.topo.shards_of(t)),
                                                STRIPE_ALIGN) * esize, 4096)
                        for t in range(self.layout.ps_tasks))
-            self.arena = McArena(self.device, need, self.rank, self.world, self._bcast)
+            # every stage is agreed on by all ranks before the next one starts: a rank
+            # that fails must not leave the others waiting in a barrier / a bind
+            try:
+                self.arena = McArena(self.device, need, self.rank, self.world, self._bcast)
+                err = None
+            except (RuntimeError, OSError) as exc:
+                err = "rank %d: %s" % (self.rank, str(exc)[:300])
+            self._agree(err)
             self.barrier()                 # every member added its device ...
-            self.arena.bind()              # ... before anyone binds memory
+            try:
+                self.arena.bind()          # ... before anyone binds memory
+                err = None
+            except RuntimeError as exc:
+                err = "rank %d: %s" % (self.rank, str(exc)[:300])
+            self._agree(err)
             self.barrier()
         self.worker = None
         self.mailbox = None
@@ -582,6 +611,28 @@ class TorchrunCluster(object):
         self.staging = None
         self.h2d_stream = self.d2h_stream = self.pull_stream = None
         self.barrier()
+
+    def _agree(self, err):
+        """All ranks learn whether any of them failed; if so everyone tears its part
+        down and raises NvlsUnavailable with the first failure's message."""
+        import torch.distributed as dist
+        errs = [err]
+        if self.world > 1:
+            errs = [None] * self.world
+            dist.all_gather_object(errs, err)
+        bad = [e for e in errs if e]
+        if not bad:
+            return
+        if self.arena is not None:
+            try:
+                self.arena.destroy()
+            except RuntimeError:
+                pass
+            self.arena = None
+        for ps in self.servers.values():
+            ps.close()
+        self.servers.clear()
+        raise NvlsUnavailable(bad[0])
 
     def _bcast(self, obj):
         import torch.distributed as dist

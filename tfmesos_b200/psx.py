@@ -245,9 +245,10 @@ class Shard(object):
         _check(lib().psx_apply_rows(self.id, int(mode), int(first_slot), int(count),
                                     int(row_len), int(wait_seq), _stream_ptr(stream)))
 
-    def serve_start(self, mode, replicas_to_aggregate=1, depth=8):
+    def serve_start(self, mode, replicas_to_aggregate=1, idle_sleep_us=0):
         """Request-free serving loop on this shard (psx_serve_start)."""
-        _check(lib().psx_serve_start(self.id, int(mode), int(replicas_to_aggregate), int(depth)))
+        _check(lib().psx_serve_start(self.id, int(mode), int(replicas_to_aggregate),
+                                     int(idle_sleep_us)))
 
     def serve_stop(self):
         _check(lib().psx_serve_stop(self.id))

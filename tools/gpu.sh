@@ -36,10 +36,10 @@ for stage in "$@"; do
     smoke)
       timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > $OUT/smoke.log 2>&1; say "smoke rc=$?"; tail -2 $OUT/smoke.log ;;
     tests)
-      ( time timeout 2400 python -m pytest tests/ -x -q -m gpu ) > $OUT/pytest_gpu.log 2>&1; say "pytest rc=$?"; tail -12 $OUT/pytest_gpu.log | cut -c1-400 ;;
+      ( time timeout 1200 python -m pytest tests/ -x -q -m gpu ) > $OUT/pytest_gpu.log 2>&1; say "pytest rc=$?"; tail -12 $OUT/pytest_gpu.log | cut -c1-400 ;;
     multirank)
       cases=${arg:-small,full,nvls}
-      ( time timeout 2400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29411 tests/multirank_parity.py --cases $cases ) > $OUT/multirank_n$N.log 2>&1; say "multirank rc=$?"
+      ( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29411 tests/multirank_parity.py --cases $cases ) > $OUT/multirank_n$N.log 2>&1; say "multirank rc=$?"
       grep -E "^CASE|MULTIRANK|rank [0-9]+\]" $OUT/multirank_n$N.log | cut -c1-300 | tail -50 ;;
     bench)
       if [ -z "$arg" ]; then
