@@ -70,6 +70,8 @@ def parse():
     p.add_argument("--worker-ranks", default=None,
                    help="ranks running a worker, e.g. '2,3,4,5' (BASELINE config #3 as "
                         "written: --ps-ranks 0,1 --worker-ranks 2,3,4,5); default: all")
+    p.add_argument("--e2e-stripes", type=int, default=32,
+                   help="shards per bucket of the host-in/host-out round (pipelining grain)")
     p.add_argument("--no-verify", action="store_true",
                    help="skip the oracle check of what was timed (\"verified\" key)")
     p.add_argument("--stripes", type=int, default=None,
@@ -211,8 +213,17 @@ def cpu_ps(args, rounds=12, warmup=2):
     psx_oracle_cpu_ps_round: memcpy push, Eigen-style threaded apply on the PS
     host cores, memcpy pull) on a bounded sample of the workload: the SAME number
     of parameters at every N, pushed and pulled by as many workers as the CUDA arm
-    has.  Persistent pinned thread pool, every range first-touched by its owning
-    thread; the reported time is the MEDIAN round."""
+    has.  Persistent pinned thread pool with work stealing, every range
+    first-touched by its owning thread.
+
+    The reported time is the BEST round.  On the pool's boxes the round time is
+    bimodal (profiles/r22, r24: ~21 ms and ~100 ms for the same 1e8-element round,
+    within one run and between runs; round 1 saw 28 ms on one box and 114 ms on
+    another) -- the host cores and memory controllers are shared with the other
+    GPUs' tenants.  The fast mode is what the host can do; taking it is both the
+    stable estimator (20.2 / 21.5 / 24.7 ms over three boxes) and the one that
+    favours the CPU arm, i.e. the conservative denominator for the headline ratio.
+    Median and every round time are reported beside it."""
     from oracle import ps_oracle as o
     n_full = n_params(args.workload)
     W = max(1, n_workers_of(args, max(1, args.gpus)))
@@ -227,16 +238,18 @@ def cpu_ps(args, rounds=12, warmup=2):
         t0 = time.perf_counter()
         threads = base.round(mode)
         times.append(time.perf_counter() - t0)
+    in_order = ["%.1f" % (t * 1e3) for t in times]
     times.sort()
-    dt = times[len(times) // 2]
+    dt, med = times[0], times[len(times) // 2]
     gbs = W * n * 8 / dt / 1e9
-    sample = ("%d of %d parameters (%.1f%%), %d worker(s), memcpy transport, median of %d "
-              "rounds (min %.1f / max %.1f ms), persistent pool pinned 1 thread/core, "
-              "first-touch by owner" % (n, n_full, 100.0 * n / n_full, W, len(times),
-                                        times[0] * 1e3, times[-1] * 1e3))
+    sample = ("%d of %d parameters (%.1f%%), %d worker(s), memcpy transport, BEST of %d rounds "
+              "(median %.1f ms = %.1f GB/s; rounds in ms: %s), persistent pool pinned 1 "
+              "thread/core, work stealing, first-touch by owner"
+              % (n, n_full, 100.0 * n / n_full, W, len(times), med * 1e3,
+                 W * n * 8 / med / 1e9, " ".join(in_order)))
     return {"value": gbs, "unit": "GB/s", "cores": int(threads), "kind": "port",
             "sample": sample, "ms_per_step_on_sample": dt * 1e3,
-            "host_cores_online": os.cpu_count()}
+            "median_GBps": W * n * 8 / med / 1e9, "host_cores_online": os.cpu_count()}
 
 
 def run_reference(args):
@@ -756,7 +769,7 @@ def run_b200(args):
     if not args.no_e2e:
         # same workload through the host-in / host-out public call; more, smaller
         # shards per bucket so H2D, the kernels and D2H pipeline across shards
-        e2e_stripes = max(16, world)
+        e2e_stripes = max(args.e2e_stripes, world)
         cl = make_cluster("staged", e2e_stripes)
         if cl.worker is not None:
             cl.staging = engine.HostStaging(cl.worker)

@@ -307,6 +307,14 @@ int psx_push_stamped(uint64_t client_id, const void *grad_dev, uint64_t off, uin
 /* Worker: the stream waits until this worker holds >= target tokens (one per
  * aggregated apply since the shard was created). */
 int psx_wait_tokens(uint64_t client_id, uint32_t target, void *stream);
+/* Host-side read of this worker's client block (sequence number of its last
+ * consumed push, tokens, mirrored global_step) through a private stream; also
+ * tells whether the shard lives in THIS process.  A process that serves a shard
+ * itself must not stream-wait on it (psx_wait_applied / psx_wait_tokens refuse
+ * with PSX_ESTATE: the wait would be submitted before the apply that satisfies
+ * it and can deadlock behind a shared hardware channel) -- it polls with this. */
+int psx_client_poll(uint64_t client_id, uint32_t *applied, uint32_t *tokens, int64_t *step,
+                    int *in_process);
 /* Worker: copy the global_step mirrored into this worker's client block by the
  * apply that consumed its last push into pinned host memory, asynchronously on
  * `stream` (the value sess.run([train_step, global_step]) returns,

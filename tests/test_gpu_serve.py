@@ -2,7 +2,13 @@
 with no host request per step -- the reference's default async discipline
 (examples/mnist/mnist_replica.py:198-205) and SyncReplicasOptimizer
 (mnist_replica.py:109-113,148-162) on the device.  Checked bit for bit against
-the oracle wherever the schedule is deterministic."""
+the oracle wherever the schedule is deterministic.
+
+PS and workers share ONE process here, so the workers wait on the host
+(``Client.wait_host``): a stream wait on a shard served by the same process is
+refused by the library (it could deadlock behind a shared hardware channel).  The
+stream-wait form runs where workers are separate processes, as in the reference:
+tests/test_gpu_examples.py (tfrun)."""
 import time
 
 import numpy as np
@@ -68,7 +74,8 @@ def test_served_async_applies_each_push_on_arrival_bit_exact():
             g = _grad(w, seqs[w])
             rig.push(w, seqs[w], g)
             c, st = rig.clients[w], rig.streams[w]
-            c.wait_applied(seqs[w], st)
+            st.synchronize()
+            c.wait_host("applied", seqs[w])
             c.pull(rig.params[w].data_ptr(), N, 0, psx.F32, 0, st)
             c.read_step_async(rig.step_host[w].data_ptr(), st)
             st.synchronize()
@@ -87,8 +94,8 @@ def test_served_async_applies_each_push_on_arrival_bit_exact():
         # ... and it keeps serving afterwards
         g = _grad(1, 99)
         rig.push(1, seqs[1] + 1, g)
-        rig.clients[1].wait_applied(seqs[1] + 1, rig.streams[1])
         rig.streams[1].synchronize()
+        rig.clients[1].wait_host("applied", seqs[1] + 1)
         ref.round(g[None, :], o.ASYNC_ORDERED)
         assert np.array_equal(rig.shard.get_values(psx.VAR).view(np.uint32), ref.var.view(np.uint32))
     finally:
@@ -110,11 +117,9 @@ def test_served_async_concurrent_pushes_are_all_consumed():
                 g = _grad(w, r)
                 total += g.astype(np.float64) * 0.05
                 rig.push(w, r, g)
-                rig.clients[w].wait_applied(r, rig.streams[w])
-                rig.clients[w].read_step_async(rig.step_host[w].data_ptr(), rig.streams[w])
             for w in range(W):
                 rig.streams[w].synchronize()
-                steps[w].append(int(rig.step_host[w][0]))
+                steps[w].append(rig.clients[w].wait_host("applied", r)["global_step"])
         stats = rig.shard.serve_stats()
         assert stats["served"] == W * R and stats["global_step"] == W * R
         flat = sorted(s for per in steps for s in per)
@@ -154,7 +159,7 @@ def test_served_sync_replicas_first_two_of_three_by_arrival_late_one_dropped():
                 rig.push(w, r, grads[w], stamp=r - 1)
                 rig.streams[w].synchronize()               # it HAS arrived
             for w in early:
-                rig.clients[w].wait_tokens(r, rig.streams[w])
+                rig.clients[w].wait_host("tokens", r)
                 rig.clients[w].pull(rig.params[w].data_ptr(), N, 0, psx.F32, 0, rig.streams[w])
                 rig.streams[w].synchronize()
             ref.round(np.stack([grads[w] for w in early]), o.SYNC_MEAN)
@@ -163,8 +168,8 @@ def test_served_sync_replicas_first_two_of_three_by_arrival_late_one_dropped():
                 assert np.array_equal(got.view(np.uint32), ref.var.view(np.uint32)), (r, w)
             # the straggler pushes a gradient computed at global_step r-1: stale now
             rig.push(late, r, grads[late], stamp=r - 1)
-            rig.clients[late].wait_tokens(r, rig.streams[late])     # its token is there already
             rig.streams[late].synchronize()
+            assert rig.clients[late].poll()["tokens"] >= r            # its token is there already
             st = _wait_stats(rig.shard, "dropped", r)
             assert st["dropped"] == r and st["global_step"] == r and st["served"] == 2 * r
         assert np.array_equal(rig.shard.get_values(psx.VAR).view(np.uint32),
@@ -192,8 +197,8 @@ def test_served_sync_all_replicas_is_the_oracle_mean_and_bf16_wire():
                 rig.push(w, r, g, stamp=r - 1)             # f32 source, cast to bf16 by the push
                 slots.append(o.bf16_to_f32(o.f32_to_bf16(g)))
             for w in range(W):
-                rig.clients[w].wait_tokens(r, rig.streams[w])
                 rig.streams[w].synchronize()
+                rig.clients[w].wait_host("tokens", r)
             ref.round(np.stack(slots), o.SYNC_MEAN)
         assert np.array_equal(rig.shard.get_values(psx.VAR).view(np.uint32),
                               ref.var.view(np.uint32))
@@ -215,8 +220,9 @@ def test_serve_stop_keeps_pushes_that_arrive_while_stopped():
         rig.streams[0].synchronize()
         assert rig.shard.serve_stats()["served"] == 0
         rig.shard.serve_start(psx.MODE_ASYNC_ORDERED)
-        rig.clients[0].wait_applied(1, rig.streams[0])
-        rig.streams[0].synchronize()
+        rig.clients[0].wait_host("applied", 1)
+        with pytest.raises(RuntimeError, match="serves the shard itself"):
+            rig.clients[0].wait_applied(1, rig.streams[0])      # refused, not a hang
         ref = o.CShard(N, o.SGD, lr=0.05)
         ref.var[:] = rig.init
         ref.round(g[None, :], o.ASYNC_ORDERED)

@@ -170,6 +170,7 @@ struct Client {
     Layout lay;
     Mapped shard;             // the PS allocation as seen from here
     ClientBlock *block = nullptr;  // in this device's HBM
+    cudaStream_t poll_stream = nullptr;   // psx_client_poll's private stream
     int sm_count = 148;
     ShardHeader *hdr() const { return (ShardHeader *)shard.base; }
     float *var() const { return (float *)(shard.base + lay.off_var()); }
@@ -1036,6 +1037,7 @@ int psx_shard_close(uint64_t id)
     cudaError_t e = cudaSetDevice(c->device);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
     close_mapped(c->shard);
+    if (c->poll_stream) cudaStreamDestroy(c->poll_stream);
     cudaError_t e2 = cudaFree(c->block);
     delete c;
     if (e == cudaSuccess) e = e2;
@@ -1249,10 +1251,14 @@ int psx_wait_mailbox(uint64_t id, uint32_t target, void *stream)
     return stream_wait_geq(stream, m->counter, target);
 }
 
+int refuse_in_process_wait(Client *c);
+
 int psx_wait_applied(uint64_t client_id, uint32_t seq, void *stream)
 {
     Client *c = find(g_clients, client_id);
     if (!c) return fail(PSX_EINVAL, "unknown client id");
+    int rc = refuse_in_process_wait(c);
+    if (rc) return rc;
     PSX_DEVICE(c->device);
     return stream_wait_geq(stream, &c->block->applied, seq);
 }
@@ -1309,12 +1315,47 @@ int psx_push_stamped(uint64_t client_id, const void *grad_dev, uint64_t off, uin
                        &c->hdr()->slot_stamp[c->slot], stamp);
 }
 
+// A stream wait on a shard that is SERVED BY THIS SAME PROCESS would be submitted
+// before the apply that satisfies it; if the two streams share a hardware channel
+// the apply queues up behind the wait for ever (see "request-free serving" above).
+// Refuse loudly instead of hanging: in-process clients poll (psx_client_poll).
+int refuse_in_process_wait(Client *c)
+{
+    if (c->shard.ipc) return PSX_OK;              // the shard lives in another process
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto &kv : g_shards)
+        if (kv.second->base == c->shard.base && kv.second->server != nullptr)
+            return fail(PSX_ESTATE, "this process serves the shard itself: a stream wait on it can "
+                                    "deadlock behind the serving stream's hardware channel -- poll "
+                                    "with psx_client_poll (workers normally live in their own process)");
+    return PSX_OK;
+}
+
 int psx_wait_tokens(uint64_t client_id, uint32_t target, void *stream)
 {
     Client *c = find(g_clients, client_id);
     if (!c) return fail(PSX_EINVAL, "unknown client id");
+    int rc = refuse_in_process_wait(c);
+    if (rc) return rc;
     PSX_DEVICE(c->device);
     return stream_wait_geq(stream, &c->block->tokens, target);
+}
+
+int psx_client_poll(uint64_t client_id, uint32_t *applied, uint32_t *tokens, int64_t *step,
+                    int *in_process)
+{
+    Client *c = find(g_clients, client_id);
+    if (!c) return fail(PSX_EINVAL, "unknown client id");
+    if (in_process) *in_process = c->shard.ipc ? 0 : 1;
+    PSX_DEVICE(c->device);
+    if (!c->poll_stream) CU_TRY(cudaStreamCreateWithFlags(&c->poll_stream, cudaStreamNonBlocking));
+    ClientBlock b;
+    CU_TRY(cudaMemcpyAsync(&b, c->block, sizeof(b), cudaMemcpyDeviceToHost, c->poll_stream));
+    CU_TRY(cudaStreamSynchronize(c->poll_stream));
+    if (applied) *applied = b.applied;
+    if (tokens) *tokens = b.tokens;
+    if (step) *step = b.step;
+    return PSX_OK;
 }
 
 int psx_read_step_async(uint64_t client_id, int64_t *host_pinned, void *stream)

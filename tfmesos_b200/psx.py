@@ -110,6 +110,8 @@ SIGNATURES = {
     "psx_push_stamped": (_i32, [_u64, _vp, _u64, _u64, _i32, _u32, _u32, _vp]),
     "psx_wait_tokens": (_i32, [_u64, _u32, _vp]),
     "psx_read_step_async": (_i32, [_u64, _vp, _vp]),
+    "psx_client_poll": (_i32, [_u64, ctypes.POINTER(_u32), ctypes.POINTER(_u32),
+                               ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(_i32)]),
     "psx_push_rows": (_i32, [_u64, _vp, _vp, _u64, _u64, _i32, _u32, _vp]),
     "psx_apply_rows": (_i32, [_u64, _i32, _i32, _i32, _u64, _u32, _vp]),
     "psx_batch": (_i32, [ctypes.POINTER(Op), _i32, ctypes.POINTER(_i32)]),
@@ -344,6 +346,26 @@ class Client(object):
 
     def wait_tokens(self, target, stream=None):
         _check(lib().psx_wait_tokens(self.id, int(target) & 0xFFFFFFFF, _stream_ptr(stream)))
+
+    def poll(self):
+        """Host-side read of the client block: {applied, tokens, global_step, in_process}."""
+        a, t, st, ip = _u32(0), _u32(0), ctypes.c_int64(0), _i32(0)
+        _check(lib().psx_client_poll(self.id, ctypes.byref(a), ctypes.byref(t), ctypes.byref(st),
+                                     ctypes.byref(ip)))
+        return {"applied": a.value, "tokens": t.value, "global_step": st.value,
+                "in_process": bool(ip.value)}
+
+    def wait_host(self, key, target, timeout=60.0):
+        """Spin on poll() until block[key] >= target (in-process clients of a served
+        shard; anything else stream-waits)."""
+        import time
+        t0 = time.time()
+        while True:
+            st = self.poll()
+            if ((st[key] - int(target)) & 0xFFFFFFFF) < 0x80000000:
+                return st
+            if time.time() - t0 > timeout:
+                raise RuntimeError("timed out waiting for %s >= %d (%r)" % (key, target, st))
 
     def read_step_async(self, host_ptr, stream=None):
         _check(lib().psx_read_step_async(self.id, host_ptr, _stream_ptr(stream)))

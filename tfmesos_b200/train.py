@@ -148,6 +148,10 @@ class ParameterClient(object):
         self._step_host = torch.zeros(1, dtype=torch.int64).pin_memory()
         self._step_event = None
         self._step_client = self.worker.clients[self.topo.shards[0].key]
+        # PS endpoints running as threads of THIS process (tests, notebooks): stream
+        # waits on a shard served in-process can deadlock (psx.h, psx_client_poll), so
+        # such a session waits on the host instead
+        self.in_process = any(c.poll()["in_process"] for c in self.worker.clients.values())
         if self.is_chief:
             for name, value in (init or {}).items():
                 self.assign(name, value)
@@ -241,8 +245,12 @@ class ParameterClient(object):
             wk.clients[spec.key].push_stamped(g.data_ptr() + spec.off * g.element_size(),
                                               spec.nelem, 0, wk.wire, self.push_seq, stamp,
                                               self.stream)
+        what = "tokens" if mode == psx.MODE_SYNC_MEAN else "applied"
         for spec in self.topo.shards:
-            if mode == psx.MODE_SYNC_MEAN:
+            if self.in_process:
+                self.stream.synchronize()          # the push has left ...
+                wk.clients[spec.key].wait_host(what, self.push_seq)   # ... and was consumed
+            elif mode == psx.MODE_SYNC_MEAN:
                 wk.clients[spec.key].wait_tokens(self.push_seq, self.stream)
             else:
                 wk.clients[spec.key].wait_applied(self.push_seq, self.stream)

@@ -19,15 +19,15 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run(workers, extra, steps):
-    cmd = [sys.executable, os.path.join(ROOT, "script", "tfrun"), "-w", str(workers), "-s", "1",
-           "--", sys.executable, os.path.join(ROOT, "examples", "mnist", "mnist_replica.py"),
+def run(workers, extra, steps, gw=0):
+    cmd = [sys.executable, os.path.join(ROOT, "script", "tfrun"), "-w", str(workers), "-s", "1"] + \
+          (["-Gw", str(gw)] if gw else []) + ["--", sys.executable, os.path.join(ROOT, "examples", "mnist", "mnist_replica.py"),
            "--ps_hosts", "{ps_hosts}", "--worker_hosts", "{worker_hosts}",
            "--job_name", "{job_name}", "--worker_index", "{task_index}",
            "--train_steps", str(steps)] + extra
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""),
                PYTHONUNBUFFERED="1")
-    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600,
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=240,
                        text=True)
     if r.returncode != 0:
         return {"error": r.stderr[-600:]}
@@ -53,11 +53,22 @@ def main():
     steps = int(os.environ.get("TFRUN_STEPS", "3000"))
     res = {"command": "tfrun -w W -s 1 -- python examples/mnist/mnist_replica.py ... "
                       "--train_steps %d (async Adam, batch 100, 784-100-10)" % steps}
+    import torch
+    n_gpus = torch.cuda.device_count()
+    res["gpus"] = n_gpus
+    res["note"] = ("1 GPU: the ps task and the worker tasks are separate PROCESSES time-slicing "
+                   "one GPU (a context switch per step each way); with -Gw 1 on >= 2 GPUs every "
+                   "worker has its own GPU and the ps task shares GPU 0 with worker 0")
+    full = os.environ.get("TFRUN_FULL", "0") == "1"
     for workers in (1, 2):
-        for name, extra in (("exact_step_numpy_batches", []),
-                            ("exact_step_device_batches", ["--device_batches"]),
-                            ("lag_step_device_batches", ["--device_batches", "--lag_step"])):
-            res["w%d/%s" % (workers, name)] = run(workers, extra, steps * workers)
+        gw = 1 if n_gpus >= workers and n_gpus >= 2 else 0
+        variants = [("exact_step_numpy_batches", []),
+                    ("lag_step_device_batches", ["--device_batches", "--lag_step"])]
+        if full:
+            variants.insert(1, ("exact_step_device_batches", ["--device_batches"]))
+        for name, extra in variants:
+            res["w%d%s/%s" % (workers, "-Gw1" if gw else "", name)] = run(
+                workers, extra + ["--quiet_steps"] * 0, steps * workers, gw)
     print(json.dumps(res, indent=1))
 
 

@@ -27,6 +27,7 @@ nvidia-smi topo -m > $OUT/topo.txt 2>&1
 PORT=29500
 trun() { PORT=$((PORT+1)); python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $PORT "${@:2}"; }
 say() { echo "$@" | tee -a $OUT/summary.txt; }
+T=${STAGE_TIMEOUT:-600}   # per-stage limit (seconds): box time is budgeted, a hang must not eat it
 BENCH_NCU_ARGS="--steps 3 --warmup 3 --no-mnist --no-cpu-baseline --no-e2e --no-staged --no-verify"
 for stage in "$@"; do
   name=${stage%%:*}; arg=""; [[ "$stage" == *:* ]] && arg=${stage#*:}
@@ -36,27 +37,27 @@ for stage in "$@"; do
     smoke)
       timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > $OUT/smoke.log 2>&1; say "smoke rc=$?"; tail -2 $OUT/smoke.log ;;
     tests)
-      ( time timeout 1200 python -m pytest tests/ -x -q -m gpu ) > $OUT/pytest_gpu.log 2>&1; say "pytest rc=$?"; tail -12 $OUT/pytest_gpu.log | cut -c1-400 ;;
+      ( time timeout $T python -m pytest tests/ -x -q -m gpu ) > $OUT/pytest_gpu.log 2>&1; say "pytest rc=$?"; tail -12 $OUT/pytest_gpu.log | cut -c1-400 ;;
     multirank)
       cases=${arg:-small,full,nvls}
-      ( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29411 tests/multirank_parity.py --cases $cases ) > $OUT/multirank_n$N.log 2>&1; say "multirank rc=$?"
+      ( time timeout $T python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29411 tests/multirank_parity.py --cases $cases ) > $OUT/multirank_n$N.log 2>&1; say "multirank rc=$?"
       grep -E "^CASE|MULTIRANK|rank [0-9]+\]" $OUT/multirank_n$N.log | cut -c1-300 | tail -50 ;;
     bench)
       if [ -z "$arg" ]; then
         if [ $N -gt 1 ]; then
-          timeout 900 bash -c "$(declare -f trun); PORT=29600; trun $N bench.py --impl reference --gpus $N --steps 20 --warmup 5" > $OUT/bench_reference_n$N.json 2> $OUT/bench_reference_n$N.err
-          ( time timeout 1500 bash -c "$(declare -f trun); PORT=29610; trun $N bench.py --gpus $N --steps 20 --warmup 5" ) > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err; say "bench rc=$?"
+          timeout $T bash -c "$(declare -f trun); PORT=29600; trun $N bench.py --impl reference --gpus $N --steps 20 --warmup 5" > $OUT/bench_reference_n$N.json 2> $OUT/bench_reference_n$N.err
+          ( time timeout $T bash -c "$(declare -f trun); PORT=29610; trun $N bench.py --gpus $N --steps 20 --warmup 5" ) > $OUT/bench_n$N.json 2> $OUT/bench_n$N.err; say "bench rc=$?"
         else
-          timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $OUT/bench_reference_n1.json 2> $OUT/bench_reference_n1.err
-          ( time timeout 1500 python bench.py --gpus 1 --steps 20 --warmup 5 ) > $OUT/bench_n1.json 2> $OUT/bench_n1.err; say "bench rc=$?"
+          timeout $T python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > $OUT/bench_reference_n1.json 2> $OUT/bench_reference_n1.err
+          ( time timeout $T python bench.py --gpus 1 --steps 20 --warmup 5 ) > $OUT/bench_n1.json 2> $OUT/bench_n1.err; say "bench rc=$?"
         fi
         cut -c1-600 $OUT/bench_reference_n$N.json; grep '^{' $OUT/bench_n$N.json | cut -c1-3000; tail -5 $OUT/bench_n$N.err
       else
         f=$OUT/bench_n${N}_$(echo "$arg" | tr -c 'a-zA-Z0-9\n' '_' | cut -c1-60)
         if [ $N -gt 1 ]; then
-          ( time timeout 1500 bash -c "$(declare -f trun); PORT=$((29700 + RANDOM % 200)); trun $N bench.py --gpus $N $extra" ) > $f.json 2> $f.err; say "bench $arg rc=$?"
+          ( time timeout $T bash -c "$(declare -f trun); PORT=$((29700 + RANDOM % 200)); trun $N bench.py --gpus $N $extra" ) > $f.json 2> $f.err; say "bench $arg rc=$?"
         else
-          ( time timeout 1500 python bench.py --gpus 1 $extra ) > $f.json 2> $f.err; say "bench $arg rc=$?"
+          ( time timeout $T python bench.py --gpus 1 $extra ) > $f.json 2> $f.err; say "bench $arg rc=$?"
         fi
         grep '^{' $f.json | cut -c1-2500; tail -5 $f.err
       fi ;;
@@ -85,13 +86,13 @@ for stage in "$@"; do
     sweep)
       f=$OUT/sweep_n${N}_$(echo "$arg" | tr -c 'a-zA-Z0-9\n' '_' | cut -c1-60)
       if [ $N -gt 1 ]; then
-        timeout 1800 bash -c "$(declare -f trun); PORT=$((29900 + RANDOM % 90)); trun $N tools/bench_sweep.py $extra" > $f.jsonl 2> $f.err; say "sweep rc=$?"
+        timeout $T bash -c "$(declare -f trun); PORT=$((29900 + RANDOM % 90)); trun $N tools/bench_sweep.py $extra" > $f.jsonl 2> $f.err; say "sweep rc=$?"
       else
-        timeout 1800 python tools/bench_sweep.py $extra > $f.jsonl 2> $f.err; say "sweep rc=$?"
+        timeout $T python tools/bench_sweep.py $extra > $f.jsonl 2> $f.err; say "sweep rc=$?"
       fi
       cut -c1-260 $f.jsonl | tail -40; tail -3 $f.err ;;
     tfrun)
-      timeout 900 python tools/bench_tfrun.py > $OUT/tfrun_mnist_replica.json 2> $OUT/tfrun_mnist_replica.err; say "tfrun rc=$?"; cat $OUT/tfrun_mnist_replica.json; tail -5 $OUT/tfrun_mnist_replica.err ;;
+      timeout $T python tools/bench_tfrun.py > $OUT/tfrun_mnist_replica.json 2> $OUT/tfrun_mnist_replica.err; say "tfrun rc=$?"; cat $OUT/tfrun_mnist_replica.json; tail -5 $OUT/tfrun_mnist_replica.err ;;
     *) say "unknown stage $stage" ;;
   esac
 done
