@@ -36,6 +36,9 @@ def main():
     ap.add_argument("--incast-workers", default="1,2,4,7")
     ap.add_argument("--max-bytes", type=int, default=int(os.environ.get("SWEEP_MAX", 1 << 30)))
     ap.add_argument("--min-bytes", type=int, default=0)
+    ap.add_argument("--sizes", default=None, help="comma list of bucket sizes in bytes "
+                    "(default: the 8 sizes 64 KB .. 1 GB)")
+    ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--wire", default="f32", choices=["f32", "bf16"])
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -53,7 +56,8 @@ def main():
     else:
         shapes = [([0], list(range(1, w + 1)), w)
                   for w in (int(x) for x in args.incast_workers.split(",")) if w + 1 <= world]
-    for nbytes in [s for s in SIZES if args.min_bytes <= s <= args.max_bytes]:
+    sizes = [int(x) for x in args.sizes.split(",")] if args.sizes else SIZES
+    for nbytes in [s for s in sizes if args.min_bytes <= s <= args.max_bytes]:
         n = nbytes // esz
         for ps_ranks, worker_ranks, W in shapes:
             for path in args.paths.split(","):
@@ -66,7 +70,7 @@ def main():
                     g = cl.worker.grad_flat[0]
                     g.copy_((torch.rand(g.numel(), device="cuda") - 0.5).to(g.dtype))
                 st = cl.worker_stream if cl.worker is not None else cl.ps_stream
-                iters = 100 if nbytes < (256 << 20) else 20
+                iters = args.iters if nbytes < (256 << 20) else max(10, args.iters // 5)
                 for _ in range(20):
                     cl.round(psx.MODE_SUM)
                 cl.barrier()
