@@ -11,7 +11,9 @@ Rank r runs on GPU ``LOCAL_RANK mod n_gpus``: on a 1-GPU box every rank shares
 GPU 0 (CUDA IPC between processes on one device), on an N-GPU box the traffic
 crosses NVLink.  Every case builds a cluster, runs a few rounds on deterministic
 gradients and compares, BIT FOR BIT (tolerance only for the NVLS cases at
-world > 2: the switch's summation order is its own),
+world > 2, where the switch's summation order is its own: the SGD cases hold the
+switch's sum itself to 2e-6, the Adam cases 99.9 % of the elements to 2e-6 and all
+of them to 5e-3 -- Adam amplifies a one-ulp change of a cancelling sum),
 
   * every hosted shard's var / m / v / beta powers / global_step with
     ``oracle.ps_oracle.CShard`` fed the same gradients (reference semantics:
@@ -115,6 +117,8 @@ def build_cases(which, world):
         cases.append(Case("mlp/nvls/f32/mean/graph", MLP, 1, path="nvls", mode="mean",
                           entry="graph", rtol=tol))
         cases.append(Case("mlp/nvls/f32/sum/sgd", MLP, 1, path="nvls", opt="sgd", rtol=tol))
+        cases.append(Case("mlp/nvls/f32/mean/sgd", MLP, 1, path="nvls", opt="sgd", mode="mean",
+                          rtol=tol))
         if "full" in which or "nvlsfull" in which:
             cases.append(Case("nmf/nvls/f32/sum/round", NMF, 2, {"W": 0, "H": 1}, path="nvls",
                               rtol=tol))
@@ -211,9 +215,23 @@ def run_case(case, rounds, rank, world, device, dist):
                 bad = np.flatnonzero(bits(got) != bits(want))
                 errors.append("%s: %d of %d elements differ (first %d: %r vs %r)"
                               % (what, bad.size, want.size, bad[0], got[bad[0]], want[bad[0]]))
-        elif not np.allclose(got, want, rtol=case.rtol, atol=case.rtol):
-            d = np.abs(got - want)
-            errors.append("%s: max abs diff %g (rtol %g)" % (what, float(d.max()), case.rtol))
+        elif case.opt == "sgd":
+            # var -= lr * g is linear in the reduced gradient: this checks the SWITCH's
+            # W-way sum itself, to about one ulp of the gradient sum
+            if not np.allclose(got, want, rtol=case.rtol, atol=case.rtol):
+                d = np.abs(got - want)
+                errors.append("%s: max abs diff %g (rtol %g)" % (what, float(d.max()), case.rtol))
+        else:
+            # Adam's step is ~alpha * sign(g) however small |g| is, so where the W-way
+            # sum cancels to within ~1e-6 of zero a one-ulp reordering of the sum moves
+            # the update by a visible fraction of lr (measured at W = 4: 1e-4 after 3
+            # rounds on < 1e-4 of the elements).  Bar: 99.9 % of the elements within
+            # 2e-6, every element within 5e-3.
+            d = np.abs(got.astype(np.float64) - want)
+            out = float(np.count_nonzero(d > case.rtol)) / max(1, d.size)
+            if out > 1e-3 or float(d.max()) > 5e-3:
+                errors.append("%s: %.2e of the elements beyond %g, max abs diff %g"
+                              % (what, out, case.rtol, float(d.max())))
 
     crcs = {}
     for key, ps in cl.servers.items():
