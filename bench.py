@@ -197,7 +197,7 @@ def parse_ranks(text):
     if text is None:
         return None
     out = []
-    for part in text.split(","):
+    for part in text.replace(":", ",").split(","):      # "0,1" or "0:1" (tools/gpu.sh splits on commas)
         rs = [int(x) for x in part.split("+")]
         out.append(rs if len(rs) > 1 else rs[0])
     return out

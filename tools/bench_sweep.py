@@ -41,6 +41,9 @@ def main():
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--wire", default="f32", choices=["f32", "bf16"])
     args = ap.parse_args()
+    for k in ("paths", "incast_workers", "sizes"):     # ":" works as the list separator too
+        if getattr(args, k):
+            setattr(args, k, getattr(args, k).replace(":", ","))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
