@@ -11,6 +11,7 @@
 #   bench:ARGS   bench.py with extra args (comma separated, e.g. bench:--path,fused,--no-mnist)
 #   launches     ncu launch list of the default bench command (1 GPU)
 #   ncufull:K    ncu --set full of kernel regex K in the default bench command (1 GPU)
+#   nvlink       ncu nvlrx/nvltx byte counters of the cross-GPU kernels, one process driving 2 GPUs
 #   sass         cuobjdump -sass extracts (UBLKCP in k_list_tma, multimem in k_round_mc)
 #   pcie         tools/bench_pcie.py on all N GPUs at once (the e2e ceiling)
 #   p2p          tools/bench_p2p.py (NVLink peaks: uni, duplex, incast, all pairs)
@@ -69,6 +70,10 @@ for stage in "$@"; do
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 6 -c 1 -o $OUT/prof_$k \
         python bench.py $BENCH_NCU_ARGS > $OUT/ncu_full_$k.log 2>&1; say "ncu full rc=$?"
       ncu -i $OUT/prof_$k.ncu-rep --page raw --csv > $OUT/prof_${k}_raw.csv 2>/dev/null ;;
+    nvlink)
+      timeout $T ncu --metrics gpu__time_duration.sum,nvlrx__bytes.sum,nvltx__bytes.sum,nvlrx__bytes_data_user.sum,nvltx__bytes_data_user.sum,dram__bytes_read.sum,dram__bytes_write.sum \
+        --clock-control none -k regex:'k_apply|k_mc_' --csv --log-file $OUT/nvlink_counters.csv \
+        python tools/prof_nvlink.py > $OUT/nvlink_counters.log 2>&1; say "ncu nvlink rc=$?"; tail -3 $OUT/nvlink_counters.log ;;
     sass)
       cuobjdump -sass tfmesos_b200/lib/libpsx.so > $OUT/libpsx.sass 2>&1
       grep -c UBLKCP $OUT/libpsx.sass | sed 's/^/UBLKCP lines: /' | tee -a $OUT/summary.txt ;;
