@@ -687,10 +687,11 @@ def run_b200(args):
         # the timer brackets the launches over the largest shard only
         bytes_per_launch = per_elem * shard_elems
         achieved = bytes_per_launch / (k_ms * 1e-3) / 1e9
-        traffic = None
+        traffic = nvl_measured = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
             traffic = tr.get("%s/%s/n%d" % (args.workload, path, world))
+            nvl_measured = tr.get("nvlink/%s" % path)
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": hbm_peak,
@@ -729,7 +730,11 @@ def run_b200(args):
                              "measured_peaks_file": "profiles/nvlink_peaks.json" if pk else None,
                              "traffic": traffic,
                              "traffic_note": "NVLink bytes are algorithmic: ncu cannot attach "
-                                             "to a multi-rank run here (profiles/README.md)",
+                                             "to a multi-rank run here; nvlink_traffic_measured "
+                                             "(when present) is ncu's nvlrx/nvltx count of this "
+                                             "kernel in a one-process 2-GPU capture, as a ratio "
+                                             "to the algorithmic bytes",
+                             "nvlink_traffic_measured": nvl_measured,
                              "hbm_achieved": achieved, "hbm_frac": achieved / hbm_peak})
     resolved_stripes = len(cl.topo.shards_of(0))
     cl.close()
