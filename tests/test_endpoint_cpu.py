@@ -107,3 +107,46 @@ def test_client_reconnects_after_the_endpoint_restarts_on_the_same_port():
         assert endpoint.call(addr, "hello")["job_name"] == "ps"
     finally:
         ep2.stop_event.set()
+
+
+def test_a_delivered_request_is_never_sent_twice():
+    """call() used to re-send after ANY socket error, so an `apply` whose
+    reply was lost ran twice (an extra global step).  Now only a send() failure on a
+    reused connection reconnects; a request that left is never repeated."""
+    from tfmesos_b200.utils import recv
+    seen = []
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(8)
+    addr = "127.0.0.1:%d" % srv.getsockname()[1]
+
+    def serve():
+        for _ in range(2):
+            try:
+                srv.settimeout(3)
+                conn, _ = srv.accept()
+            except OSError:
+                return
+            try:
+                seen.append(recv(conn))        # take the request ...
+            except Exception:
+                pass
+            conn.close()                       # ... and drop the connection without replying
+
+    t = threading.Thread(target=serve)
+    t.daemon = True
+    t.start()
+    with pytest.raises((OSError, AssertionError, EOFError)):
+        endpoint.call(addr, "apply", key=(0, 0))
+    t.join(5)
+    srv.close()
+    assert len(seen) == 1 and seen[0][0] == "apply"
+
+
+def test_call_only_runs_allow_listed_modules():
+    cluster_def, eps = _start(1, 0)
+    try:
+        with pytest.raises(RuntimeError, match="TFMESOS_CALL_MODULES"):
+            endpoint.call(cluster_def["ps"][0], "call", fn="os:getcwd", kwargs={})
+    finally:
+        _stop(eps)
