@@ -82,6 +82,8 @@ def parse():
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-staged", action="store_true")
     p.add_argument("--no-mnist", action="store_true")
+    p.add_argument("--no-tfrun", action="store_true",
+                   help="skip the tfrun / one-process-per-task MNIST step timing (N = 1 only)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample-elems", type=int, default=100_000_000,
                    help="CPU arms: parameters per step -- the SAME absolute sample at every "
@@ -821,6 +823,30 @@ def run_b200(args):
         mnist = mnist_section(torch, engine, psx, world, rank, dist, "mlp")
         softmax = mnist_section(torch, engine, psx, world, rank, dist, "softmax")
 
+    # the LITERAL reference-API path next to the graph-captured one: tfrun + one OS
+    # process per ps / worker task + examples/mnist/mnist_replica.py, request-free
+    # async (tools/bench_tfrun.py).  1-GPU runs only: the tasks need the GPU to
+    # themselves (this process is idle meanwhile), and it is a per-box latency figure.
+    tfrun_api = None
+    if rank == 0 and world == 1 and not args.no_mnist and not args.no_tfrun:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_tfrun
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            tfrun_api = {"command": "tfrun -w 1 -s 1 -- python examples/mnist/mnist_replica.py "
+                                    "... --train_steps 1500 (one process per task, async Adam)"}
+            for name, extra in (("as_the_reference_feeds_it(numpy batches, exact global_step)", []),
+                                ("device_batches_lagged_step", ["--device_batches", "--lag_step"])):
+                r = bench_tfrun.run(1, extra, 1500, timeout=90)
+                tfrun_api[name] = ({"ms_per_step": r.get("ms_per_chief_step_median"),
+                                    "steps_per_sec": (1e3 / r["ms_per_chief_step_median"]
+                                                      if r.get("ms_per_chief_step_median") else None),
+                                    "final_global_step": r.get("final_global_step")}
+                                   if "error" not in r else {"error": r["error"][-200:]})
+        except Exception as exc:                   # never lose the bench line over this
+            tfrun_api = {"error": str(exc)[:200]}
+
     cpu = cpu_grpc = None
     if rank == 0 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)          # the CPU arm gets every host core
@@ -863,6 +889,7 @@ def run_b200(args):
             "cpu_baseline_grpc": cpu_grpc,
             "mnist_replica": mnist,
             "mnist_softmax_sgd": softmax,
+            "mnist_replica_via_tfrun": tfrun_api,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -19,7 +19,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run(workers, extra, steps, gw=0):
+def run(workers, extra, steps, gw=0, timeout=240):
     cmd = [sys.executable, os.path.join(ROOT, "script", "tfrun"), "-w", str(workers), "-s", "1"] + \
           (["-Gw", str(gw)] if gw else []) + ["--", sys.executable, os.path.join(ROOT, "examples", "mnist", "mnist_replica.py"),
            "--ps_hosts", "{ps_hosts}", "--worker_hosts", "{worker_hosts}",
@@ -27,8 +27,20 @@ def run(workers, extra, steps, gw=0):
            "--train_steps", str(steps)] + extra
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""),
                PYTHONUNBUFFERED="1")
-    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=240,
-                       text=True)
+    import signal
+    from types import SimpleNamespace
+    p = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                         start_new_session=True)
+    try:
+        out, err = p.communicate(timeout=timeout)
+    except subprocess.TimeoutExpired:
+        try:
+            os.killpg(p.pid, signal.SIGKILL)       # exactly the process group started above
+        except OSError:
+            pass
+        p.communicate()
+        return {"error": "tfrun did not finish within %d s" % timeout}
+    r = SimpleNamespace(returncode=p.returncode, stdout=out, stderr=err)
     if r.returncode != 0:
         return {"error": r.stderr[-600:]}
     stamps = [float(m.group(1)) for m in
