@@ -229,3 +229,43 @@ def test_serve_stop_keeps_pushes_that_arrive_while_stopped():
         assert np.array_equal(rig.shard.get_values(psx.VAR).view(np.uint32), ref.var.view(np.uint32))
     finally:
         rig.close()
+
+
+def test_accessors_from_several_threads_pause_the_loop_one_at_a_time():
+    """Endpoint handler threads call state() / get_values() concurrently while the
+    shard is served (every worker asks for global_step at the end of training): the
+    pause / resume of the loop is serialised per shard, nothing is lost."""
+    import threading
+    rig = _Rig(2, psx.OPT_SGD, 0.05)
+    errors = []
+    try:
+        rig.shard.serve_start(psx.MODE_ASYNC_ORDERED, idle_sleep_us=20)
+
+        def hammer():
+            try:
+                for _ in range(8):
+                    st = rig.shard.state()
+                    assert st["global_step"] >= 0
+                    rig.shard.get_values(psx.VAR, 0, 16)
+            except Exception as exc:           # noqa: BLE001 - reported below
+                errors.append(repr(exc))
+
+        threads = [threading.Thread(target=hammer) for _ in range(4)]
+        for t in threads:
+            t.start()
+        total = np.zeros(N, np.float64)
+        for r in range(1, 9):
+            for w in range(2):
+                g = _grad(w, r)
+                total += g.astype(np.float64) * 0.05
+                rig.push(w, r, g)
+            for w in range(2):
+                rig.streams[w].synchronize()
+                rig.clients[w].wait_host("applied", r)
+        for t in threads:
+            t.join(60)
+        assert not errors, errors
+        assert rig.shard.serve_stats()["served"] == 16
+        np.testing.assert_allclose(rig.shard.get_values(psx.VAR), rig.init - total, rtol=0, atol=2e-5)
+    finally:
+        rig.close()

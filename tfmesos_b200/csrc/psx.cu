@@ -146,6 +146,8 @@ struct Server;
 struct Shard {
     int device = 0;
     Server *server = nullptr;         // request-free serving loop (psx_serve_start)
+    std::recursive_mutex serve_mu;    // start / stop / pause of that loop: accessors may come
+                                      // from several endpoint threads at once
     Layout lay;
     char *base = nullptr;
     int sm_count = 148;
@@ -547,9 +549,10 @@ int serve_stop_impl(Shard *s, int *mode, int *aggregate, int *idle_sleep_us)
 // var / m / v / state, and no apply is launched under a host copy.
 struct ServePause {
     Shard *s;
+    std::unique_lock<std::recursive_mutex> lk;    // held for the accessor's whole duration
     bool was = false;
     int mode = 0, aggregate = 1, depth = 0, rc = PSX_OK;
-    explicit ServePause(Shard *sh) : s(sh)
+    explicit ServePause(Shard *sh) : s(sh), lk(sh->serve_mu)
     {
         if (s->server) {
             was = true;
@@ -684,7 +687,11 @@ int psx_shard_destroy(uint64_t id)
         s = it->second;
         g_shards.erase(it);
     }
-    int src = serve_stop_impl(s, nullptr, nullptr, nullptr);
+    int src;
+    {
+        std::lock_guard<std::recursive_mutex> lk(s->serve_mu);
+        src = serve_stop_impl(s, nullptr, nullptr, nullptr);
+    }
     cudaError_t e = cudaSetDevice(s->device);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();   // a failed kernel surfaces here
     for (int c = 0; c < PSX_MAX_SLOTS; ++c) {
@@ -1268,6 +1275,7 @@ int psx_serve_start(uint64_t shard_id, int mode, int replicas_to_aggregate, int 
 {
     Shard *s = find(g_shards, shard_id);
     if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    std::lock_guard<std::recursive_mutex> lk(s->serve_mu);
     return serve_start_impl(s, mode, replicas_to_aggregate, idle_sleep_us);
 }
 
@@ -1275,6 +1283,7 @@ int psx_serve_stop(uint64_t shard_id)
 {
     Shard *s = find(g_shards, shard_id);
     if (!s) return fail(PSX_EINVAL, "unknown shard id");
+    std::lock_guard<std::recursive_mutex> lk(s->serve_mu);
     return serve_stop_impl(s, nullptr, nullptr, nullptr);
 }
 
@@ -1283,7 +1292,10 @@ int psx_serve_stats(uint64_t shard_id, uint64_t *iterations, uint32_t *served, u
 {
     Shard *s = find(g_shards, shard_id);
     if (!s) return fail(PSX_EINVAL, "unknown shard id");
-    if (iterations) *iterations = s->server ? s->server->iterations.load() : 0;
+    {
+        std::lock_guard<std::recursive_mutex> lk(s->serve_mu);
+        if (iterations) *iterations = s->server ? s->server->iterations.load() : 0;
+    }
     PSX_DEVICE(s->device);
     // a plain copy on its own stream: does not wait for the queued iterations
     cudaStream_t side = nullptr;
