@@ -83,3 +83,108 @@ def test_gpu_arm_fails_loudly_without_a_gpu():
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
     assert r.returncode != 0
     assert b"no CUDA device" in r.stderr + r.stdout
+
+
+ARENA_WORKER = r'''
+import json, os, sys
+sys.path.insert(0, %r)
+import torch.distributed as dist
+from tfmesos_b200 import engine, psx
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+FAIL = os.environ.get("FAIL_RANK", "")
+
+
+class FakeMember(object):
+    """psx.McMember without CUDA: the 'multicast object' is a pipe whose write end the
+    creator keeps; importing = receiving a descriptor that refers to the same pipe."""
+    def __init__(self, fd, created):
+        self.fd, self.created, self.added = fd, created, False
+    @classmethod
+    def create(cls, device, n, nbytes):
+        if FAIL == "create":
+            raise RuntimeError("cuMulticastCreate failed (simulated)")
+        r, w = os.pipe()
+        os.write(w, b"mc-object-of-%%d-members" %% n)
+        cls.keep = w
+        return cls(r, True)
+    @classmethod
+    def import_fd(cls, device, n, nbytes, fd):
+        if FAIL == str(rank):
+            raise RuntimeError("cuMemImportFromShareableHandle failed (simulated)")
+        m = cls(os.dup(fd), False)
+        return m
+    def add_device(self):
+        self.added = True
+    def bind(self):
+        return 0x1000, 0x2000, 1 << 20
+    def destroy(self):
+        os.close(self.fd)
+
+
+psx.McMember = FakeMember
+
+
+def bcast(obj):
+    box = [obj]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+out = {"rank": rank}
+try:
+    arena = engine.McArena(0, 1 << 20, rank, world, bcast)
+    out["err"] = None
+except (RuntimeError, OSError) as exc:
+    arena, out["err"] = None, str(exc)
+errs = [None] * world
+dist.all_gather_object(errs, out["err"])
+out["all_errs"] = errs
+if arena is not None and not any(errs):
+    # every member's descriptor refers to the SAME object (fstat identity of the pipe)
+    st = os.fstat(arena.mcx.fd)
+    ids = [None] * world
+    dist.all_gather_object(ids, (st.st_dev, st.st_ino))
+    out["same_object"] = len(set(ids)) == 1
+    out["added"] = arena.mcx.added
+    arena.bind()
+    out["size"] = arena.size
+    arena.destroy()
+elif arena is not None:
+    arena.destroy()
+with open(os.path.join(os.environ["OUT_DIR"], "arena%%d.json" %% rank), "w") as f:
+    json.dump(out, f)
+dist.barrier()
+dist.destroy_process_group()
+''' % ROOT
+
+
+def _run_arena(tmp_path, world, fail, port):
+    script = tmp_path / "a.py"
+    script.write_text(ARENA_WORKER)
+    env = dict(os.environ, OUT_DIR=str(tmp_path), FAIL_RANK=fail)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), str(script)],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=240)
+    assert r.returncode == 0, r.stderr.decode()[-2500:]
+    return [json.load(open(tmp_path / ("arena%d.json" % k))) for k in range(world)]
+
+
+def test_multicast_descriptor_reaches_every_rank_over_scm_rights(tmp_path):
+    """engine.McArena's plumbing without CUDA: rank 0 'creates' the multicast object,
+    its descriptor travels to the other PROCESSES over an abstract AF_UNIX socket
+    (SCM_RIGHTS), every rank ends up holding the same kernel object and adds itself."""
+    outs = _run_arena(tmp_path, 3, "", 29671)
+    assert all(o["err"] is None for o in outs)
+    assert all(o["same_object"] and o["added"] and o["size"] == 1 << 20 for o in outs)
+
+
+@pytest.mark.parametrize("fail", ["create", "2"])
+def test_a_failing_rank_does_not_leave_the_others_waiting(tmp_path, fail):
+    """NVLS is chosen once, at set-up: if building the team fails on ANY rank (here:
+    the creator, or an importer), every rank gets out of the exchange and learns about
+    it (TorchrunCluster._agree turns that into NvlsUnavailable on all of them)."""
+    outs = _run_arena(tmp_path, 3, fail, 29672 if fail == "create" else 29673)
+    assert any(o["err"] for o in outs)
+    assert all(any(o["all_errs"]) for o in outs)          # everybody knows
