@@ -70,8 +70,10 @@ def parse():
     p.add_argument("--worker-ranks", default=None,
                    help="ranks running a worker, e.g. '2,3,4,5' (BASELINE config #3 as "
                         "written: --ps-ranks 0,1 --worker-ranks 2,3,4,5); default: all")
-    p.add_argument("--e2e-stripes", type=int, default=32,
-                   help="shards per bucket of the host-in/host-out round (pipelining grain)")
+    p.add_argument("--e2e-stripes", type=int, default=None,
+                   help="shards per bucket of the host-in/host-out round (pipelining grain; "
+                        "default 16 on one GPU -- measured 90.4 vs 87.7 GB/s with 32, profiles/"
+                        "r24, r29 -- and 32 from 2 GPUs, where every GPU hosts 1/N of them)")
     p.add_argument("--no-verify", action="store_true",
                    help="skip the oracle check of what was timed (\"verified\" key)")
     p.add_argument("--stripes", type=int, default=None,
@@ -218,14 +220,13 @@ def cpu_ps(args, rounds=12, warmup=2):
     has.  Persistent pinned thread pool with work stealing, every range
     first-touched by its owning thread.
 
-    The reported time is the BEST round.  On the pool's boxes the round time is
-    bimodal (profiles/r22, r24: ~21 ms and ~100 ms for the same 1e8-element round,
-    within one run and between runs; round 1 saw 28 ms on one box and 114 ms on
-    another) -- the host cores and memory controllers are shared with the other
-    GPUs' tenants.  The fast mode is what the host can do; taking it is both the
-    stable estimator (20.2 / 21.5 / 24.7 ms over three boxes) and the one that
-    favours the CPU arm, i.e. the conservative denominator for the headline ratio.
-    Median and every round time are reported beside it."""
+    The pool has as many threads as the container can actually run: the CPUs in
+    its affinity mask capped by its cgroup CPU quota.  The pool's GPU boxes show 128
+    CPUs but give the container a 16-core CFS quota; with 128 threads the round time
+    was bimodal (7-20 ms inside the quota, 40-100 ms once throttled until the next
+    100 ms period -- profiles/r22-r29, explained by profiles/r30: `nr_throttled`
+    climbs), with 16 threads it is 15.0 +- 0.1 ms.  Reported: the MEDIAN round,
+    with every round time in `sample`; `cores` = the threads that ran."""
     from oracle import ps_oracle as o
     n_full = n_params(args.workload)
     W = max(1, n_workers_of(args, max(1, args.gpus)))
@@ -242,16 +243,19 @@ def cpu_ps(args, rounds=12, warmup=2):
         times.append(time.perf_counter() - t0)
     in_order = ["%.1f" % (t * 1e3) for t in times]
     times.sort()
-    dt, med = times[0], times[len(times) // 2]
+    dt = times[len(times) // 2]
     gbs = W * n * 8 / dt / 1e9
-    sample = ("%d of %d parameters (%.1f%%), %d worker(s), memcpy transport, BEST of %d rounds "
-              "(median %.1f ms = %.1f GB/s; rounds in ms: %s), persistent pool pinned 1 "
-              "thread/core, work stealing, first-touch by owner"
-              % (n, n_full, 100.0 * n / n_full, W, len(times), med * 1e3,
-                 W * n * 8 / med / 1e9, " ".join(in_order)))
+    quota = o.cpu_quota_cores()
+    sample = ("%d of %d parameters (%.1f%%), %d worker(s), memcpy transport, MEDIAN of %d rounds "
+              "(best %.1f ms; rounds in ms: %s); pool of %d pinned threads = CPUs usable by the "
+              "container (%d in the affinity mask, CPU quota %s cores), work stealing, "
+              "first-touch by owner"
+              % (n, n_full, 100.0 * n / n_full, W, len(times), times[0] * 1e3,
+                 " ".join(in_order), int(threads), len(os.sched_getaffinity(0)),
+                 ("%.0f" % quota) if quota else "none"))
     return {"value": gbs, "unit": "GB/s", "cores": int(threads), "kind": "port",
             "sample": sample, "ms_per_step_on_sample": dt * 1e3,
-            "median_GBps": W * n * 8 / med / 1e9, "host_cores_online": os.cpu_count()}
+            "cpu_quota_cores": quota, "host_cores_online": os.cpu_count()}
 
 
 def run_reference(args):
@@ -781,7 +785,7 @@ def run_b200(args):
     if not args.no_e2e:
         # same workload through the host-in / host-out public call; more, smaller
         # shards per bucket so H2D, the kernels and D2H pipeline across shards
-        e2e_stripes = max(args.e2e_stripes, world)
+        e2e_stripes = max(args.e2e_stripes or (16 if world == 1 else 32), world)
         cl = make_cluster("staged", e2e_stripes)
         if cl.worker is not None:
             cl.staging = engine.HostStaging(cl.worker)

@@ -336,19 +336,58 @@ class CShard:
         assert rc == 0, rc
 
 
+def cpu_quota_cores(root="/sys/fs/cgroup"):
+    """CPU bandwidth the container may use, in cores (cgroup v2 ``cpu.max`` or v1
+    ``cpu.cfs_quota_us / cpu.cfs_period_us``); None when unlimited.  The pool's GPU
+    boxes show 128 CPUs but run their containers under a 16-core CFS quota: 128
+    busy threads exhaust it within each 100 ms period and are throttled until the
+    next one -- the "bimodal" 7 ms / 100 ms rounds of profiles/r22-r29
+    (``nr_throttled`` climbs, profiles/r30).  A pool of exactly `quota` threads is
+    never throttled: 15.0 +- 0.1 ms for the same round."""
+    try:
+        txt = open(os.path.join(root, "cpu.max")).read().split()
+        if txt and txt[0] != "max":
+            return float(txt[0]) / float(txt[1])
+        if txt:
+            return None
+    except (OSError, ValueError, IndexError):
+        pass
+    try:
+        q = int(open(os.path.join(root, "cpu", "cpu.cfs_quota_us")).read())
+        p = int(open(os.path.join(root, "cpu", "cpu.cfs_period_us")).read())
+        if q > 0 and p > 0:
+            return q / float(p)
+    except (OSError, ValueError):
+        pass
+    return None
+
+
+def usable_threads():
+    """Threads worth running: the CPUs this process may be scheduled on, capped by
+    the container's CPU quota."""
+    n = len(os.sched_getaffinity(0))
+    q = cpu_quota_cores()
+    if q is not None:
+        n = max(1, min(n, int(q)))
+    return n
+
+
 class CpuPsBaseline:
     """Multi-threaded CPU-PS round (memcpy push, apply, memcpy pull) used as the
     timed CPU baseline by bench.py.  The arrays come untouched from the
     allocator and are FIRST-TOUCHED by the pool thread that owns each range in
     every later round (psx_oracle_cpu_ps_init), so NUMA placement is the same on
-    every run; the pool is persistent and its threads are pinned."""
+    every run; the pool is persistent, its threads are pinned, and it is sized to
+    the container's CPU quota (usable_threads)."""
 
     def __init__(self, nelem, W, opt=ADAM, lr=0.01, b1=0.9, b2=0.999, eps=1e-8,
                  threads=0):
         self.lib = c_lib()
         self.n, self.W, self.opt = int(nelem), int(W), opt
         self.hyper = (float(F(lr)), float(F(b1)), float(F(b2)), float(F(eps)))
-        self.threads = self.lib.psx_oracle_pool_start(int(threads))
+        # threads = 0: as many as the container can actually run (affinity capped by
+        # its CPU quota)
+        self.threads = self.lib.psx_oracle_pool_start(int(threads) if threads else usable_threads())
         assert self.threads > 0, "thread pool failed to start (%d)" % self.threads
         self.var = np.empty(self.n, F)           # np.empty: pages not touched yet
         self.m = np.empty(self.n, F)

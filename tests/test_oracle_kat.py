@@ -207,3 +207,20 @@ def test_sgd_matches_torch_optim_sgd_and_adam_differs_from_torch_adam():
         tq.grad = torch.tensor(small)
         topt.step()
     assert not np.allclose(a.var, tq.detach().numpy(), rtol=1e-3, atol=0)
+
+
+def test_cpu_quota_is_read_from_cgroup_v2_and_v1(tmp_path):
+    """The CPU arm sizes its thread pool to the container's CPU quota (the GPU boxes
+    show 128 CPUs under a 16-core CFS quota: profiles/r30)."""
+    (tmp_path / "cpu.max").write_text("1600000 100000\n")
+    assert o.cpu_quota_cores(str(tmp_path)) == 16.0
+    (tmp_path / "cpu.max").write_text("max 100000\n")
+    assert o.cpu_quota_cores(str(tmp_path)) is None
+    v1 = tmp_path / "v1"
+    (v1 / "cpu").mkdir(parents=True)
+    (v1 / "cpu" / "cpu.cfs_quota_us").write_text("-1\n")
+    (v1 / "cpu" / "cpu.cfs_period_us").write_text("100000\n")
+    assert o.cpu_quota_cores(str(v1)) is None
+    (v1 / "cpu" / "cpu.cfs_quota_us").write_text("250000\n")
+    assert o.cpu_quota_cores(str(v1)) == 2.5
+    assert 1 <= o.usable_threads() <= len(__import__("os").sched_getaffinity(0))
