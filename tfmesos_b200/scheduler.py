@@ -35,7 +35,7 @@ import threading
 import time
 import uuid
 
-from .utils import AttrDict, local_hostname, recv, send, setup_logger
+from .utils import AttrDict, bind_advertised, local_hostname, recv, send, setup_logger
 
 FOREVER = 0xFFFFFFFF
 TERMINAL_STATES = ('TASK_FINISHED', 'TASK_FAILED', 'TASK_KILLED', 'TASK_ERROR')
@@ -227,7 +227,7 @@ class TFMesosScheduler(object):
         listener = socket.socket()
         try:
             listener.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
-            listener.bind(('', 0))
+            bind_advertised(listener)
             self.addr = '%s:%s' % (local_hostname(), listener.getsockname()[1])
             listener.listen(64)
             framework = AttrDict(user=getpass.getuser(), name=self.name,

@@ -18,7 +18,7 @@ import socket
 import subprocess
 import sys
 
-from .utils import local_hostname, recv, send
+from .utils import bind_advertised, local_hostname, recv, send
 
 logger = logging.getLogger(__name__)
 
@@ -28,7 +28,7 @@ def reserve_port():
     next, as the reference does for TF's gRPC server (server.py:18-21)."""
     fd = socket.socket()
     fd.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
-    fd.bind(('', 0))
+    bind_advertised(fd)
     return fd, '%s:%s' % (local_hostname(), fd.getsockname()[1])
 
 

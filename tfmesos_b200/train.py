@@ -17,6 +17,7 @@ import time
 from contextlib import contextmanager
 
 from . import endpoint, engine, psx
+from .utils import bind_advertised
 from .engine import (AdamOptimizer, GradientDescentOptimizer,  # noqa: F401
                      replica_device_setter)
 
@@ -50,7 +51,7 @@ class Server(object):
         port = int(addr.rsplit(':', 1)[1])
         self.listener = socket.socket()
         self.listener.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
-        self.listener.bind(('', port))
+        bind_advertised(self.listener, port, addr.rsplit(':', 1)[0])
         self.endpoint = endpoint.Endpoint(job_name, self.task_index, cluster.jobs, gpus=gpus)
 
     def join(self):

@@ -85,3 +85,22 @@ def local_hostname():
         return name
     except socket.error:
         return '127.0.0.1'
+
+
+def bind_advertised(sock, port=0, host=None):
+    """Bind ``sock`` to the address this box ADVERTISES (``local_hostname()``, or the
+    host part of a cluster-spec address) instead of every interface: the control
+    sockets unpickle what they receive and the task endpoint runs what its client
+    asks for, so nothing off the box has any business connecting.  The
+    reference binds ``''`` (server.py:18-21, scheduler.py:328-333); set
+    ``TFMESOS_BIND=all`` for that.  Falls back to ``''`` if the advertised name
+    cannot be bound here (a hostname that resolves to a foreign address)."""
+    import os
+    host = local_hostname() if host is None else host
+    if os.environ.get('TFMESOS_BIND', 'advertised') != 'all':
+        try:
+            sock.bind((host, port))
+            return
+        except OSError:
+            pass
+    sock.bind(('', port))
