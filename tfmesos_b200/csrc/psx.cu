@@ -1360,7 +1360,10 @@ int psx_client_poll(uint64_t client_id, uint32_t *applied, uint32_t *tokens, int
     if (!c) return fail(PSX_EINVAL, "unknown client id");
     if (in_process) *in_process = c->shard.ipc ? 0 : 1;
     PSX_DEVICE(c->device);
-    if (!c->poll_stream) CU_TRY(cudaStreamCreateWithFlags(&c->poll_stream, cudaStreamNonBlocking));
+    {
+        std::lock_guard<std::mutex> lk(g_mu);     // two pollers must not both create it
+        if (!c->poll_stream) CU_TRY(cudaStreamCreateWithFlags(&c->poll_stream, cudaStreamNonBlocking));
+    }
     ClientBlock b;
     CU_TRY(cudaMemcpyAsync(&b, c->block, sizeof(b), cudaMemcpyDeviceToHost, c->poll_stream));
     CU_TRY(cudaStreamSynchronize(c->poll_stream));
