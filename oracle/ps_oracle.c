@@ -159,6 +159,60 @@ int psx_oracle_round_adam(float *var, float *m, float *v, const float *slots,
     return 0;
 }
 
+/* ---- index-list (IndexedSlices) round: second restatement of ps_oracle.py rows_round
+ * The shard is a [n_rows, d] matrix.  Worker w contributes k[w] rows with STRICTLY
+ * ASCENDING row indices idx[w][0..k[w]) and gradients rows[w] (k[w] x d).  A row
+ * pushed by several workers gets ((g_w + g_w') + ...) in worker order; mean != 0
+ * divides by W; SGD / Adam (stored powers, not advanced here) are applied ONCE to
+ * every touched row; untouched rows keep var / m / v.  (the NMF row
+ * blocks of examples/matrix_factorization.py:21-28,43-49.)  Returns -1 on a
+ * non-ascending list or an index outside the matrix. */
+static long rows_find(const int64_t *idx, long n, int64_t key)
+{
+    long lo = 0, hi = n;
+    while (lo < hi) {
+        long mid = (lo + hi) / 2;
+        if (idx[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return (lo < n && idx[lo] == key) ? lo : -1;
+}
+
+int psx_oracle_rows_round(float *var, float *m, float *v, size_t n_rows, size_t d, int W,
+                          const int64_t *const *idx, const float *const *rows, const size_t *k,
+                          int opt_adam, int mean, float lr, float b1, float b2, float eps,
+                          float b1p, float b2p, float *scratch /* d floats */)
+{
+    for (int w = 0; w < W; ++w)
+        for (size_t j = 0; j < k[w]; ++j) {
+            if (idx[w][j] < 0 || (size_t)idx[w][j] >= n_rows) return -1;
+            if (j > 0 && idx[w][j] <= idx[w][j - 1]) return -1;
+        }
+    for (int w = 0; w < W; ++w) {
+        for (size_t j = 0; j < k[w]; ++j) {
+            const int64_t r = idx[w][j];
+            int first = 1;                       /* is w the lowest worker holding row r? */
+            for (int w2 = 0; w2 < w && first; ++w2)
+                if (rows_find(idx[w2], (long)k[w2], r) >= 0) first = 0;
+            if (!first) continue;
+            for (size_t e = 0; e < d; ++e) scratch[e] = rows[w][j * d + e];
+            for (int w2 = w + 1; w2 < W; ++w2) {
+                long p = rows_find(idx[w2], (long)k[w2], r);
+                if (p < 0) continue;
+                for (size_t e = 0; e < d; ++e) scratch[e] = scratch[e] + rows[w2][(size_t)p * d + e];
+            }
+            if (mean)
+                for (size_t e = 0; e < d; ++e) scratch[e] = scratch[e] / (float)W;
+            if (opt_adam)
+                psx_oracle_adam(var + (size_t)r * d, m + (size_t)r * d, v + (size_t)r * d, scratch, d,
+                                lr, b1, b2, eps, b1p, b2p);
+            else
+                psx_oracle_sgd(var + (size_t)r * d, scratch, d, lr);
+        }
+    }
+    return 0;
+}
+
 /* ---- bf16 wire format (BASELINE config #4: grads pushed / params pulled bf16)
  * round-to-nearest-even float -> bf16, NaN kept quiet; matches
  * __float2bfloat16_rn on the device. */

@@ -270,6 +270,11 @@ def c_lib():
     lib.psx_oracle_cast_f32_bf16.restype = None
     lib.psx_oracle_cast_bf16_f32.argtypes = [fp, u16p, sz]
     lib.psx_oracle_cast_bf16_f32.restype = None
+    i64pp = ctypes.POINTER(ctypes.POINTER(ctypes.c_int64))
+    lib.psx_oracle_rows_round.argtypes = [fp, fp, fp, sz, sz, ctypes.c_int, i64pp,
+                                          ctypes.POINTER(fp), ctypes.POINTER(sz), ctypes.c_int,
+                                          ctypes.c_int, fl, fl, fl, fl, fl, fl, fp]
+    lib.psx_oracle_rows_round.restype = ctypes.c_int
     lib.psx_oracle_threads.restype = ctypes.c_int
     fpp = ctypes.POINTER(fp)
     lib.psx_oracle_cpu_ps_round.argtypes = [fp, fp, fp, fp, sz, fpp, fpp,
@@ -370,6 +375,31 @@ def usable_threads():
     if q is not None:
         n = max(1, min(n, int(q)))
     return n
+
+
+def c_rows_round(shard, row_len, idx_lists, row_lists, mode):
+    """:func:`rows_round` by ps_oracle.c (the second restatement) on a :class:`CShard`."""
+    assert mode in (SUM, SYNC_MEAN)
+    lib = c_lib()
+    W = len(idx_lists)
+    idx = [np.ascontiguousarray(i, np.int64) for i in idx_lists]
+    rows = [np.ascontiguousarray(r, F).reshape(-1, row_len) for r in row_lists]
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    fp = ctypes.POINTER(ctypes.c_float)
+    pi = (i64p * W)(*[a.ctypes.data_as(i64p) for a in idx])
+    pr = (fp * W)(*[a.ctypes.data_as(fp) for a in rows])
+    k = (ctypes.c_size_t * W)(*[a.size for a in idx])
+    lr, b1, b2, eps = shard.hyper
+    scratch = np.zeros(row_len, F)
+    rc = lib.psx_oracle_rows_round(_fp(shard.var), _fp(shard.m), _fp(shard.v),
+                                   shard.n // row_len, row_len, W, pi, pr, k,
+                                   int(shard.opt == ADAM), int(mode == SYNC_MEAN), lr, b1, b2, eps,
+                                   float(shard.state[0]), float(shard.state[1]), _fp(scratch))
+    assert rc == 0, "indices must be strictly ascending and inside the matrix"
+    if shard.opt == ADAM:
+        shard.state[0] = F(shard.state[0] * F(b1))
+        shard.state[1] = F(shard.state[1] * F(b2))
+    shard._step.value += 1
 
 
 class CpuPsBaseline:

@@ -224,3 +224,45 @@ def test_cpu_quota_is_read_from_cgroup_v2_and_v1(tmp_path):
     (v1 / "cpu" / "cpu.cfs_quota_us").write_text("250000\n")
     assert o.cpu_quota_cores(str(v1)) == 2.5
     assert 1 <= o.usable_threads() <= len(__import__("os").sched_getaffinity(0))
+
+
+@pytest.mark.parametrize("opt", [o.SGD, o.ADAM])
+@pytest.mark.parametrize("mode", [o.SUM, o.SYNC_MEAN])
+def test_sparse_rows_round_numpy_and_c_restatements_agree_and_match_a_hand_case(opt, mode):
+    """Index-list (IndexedSlices) round, SURVEY 8f-3: the two restatements agree bit
+    for bit on overlapping random lists; rows nobody pushed are untouched; a hand
+    case: two workers pushing the same row are summed in worker order."""
+    n_rows, d, W = 300, 12, 3
+    rng = np.random.default_rng(4)
+    a = o.Shard(n_rows * d, opt, lr=0.05)
+    b = o.CShard(n_rows * d, opt, lr=0.05)
+    init = rng.standard_normal(n_rows * d).astype(F)
+    a.var[:] = init
+    b.var[:] = init
+    touched = set()
+    for _ in range(3):
+        idx, rows = [], []
+        for w in range(W):
+            i = np.sort(rng.choice(n_rows, size=int(rng.integers(1, 80)), replace=False))
+            idx.append(i.astype(np.int64))
+            rows.append((rng.standard_normal((i.size, d)) * 0.1).astype(F))
+            touched |= set(i.tolist())
+        o.rows_round(a, d, idx, rows, mode)
+        o.c_rows_round(b, d, idx, rows, mode)
+    assert np.array_equal(a.var.view(np.uint32), b.var.view(np.uint32))
+    assert np.array_equal(a.m.view(np.uint32), b.m.view(np.uint32))
+    assert np.array_equal(a.v.view(np.uint32), b.v.view(np.uint32))
+    assert a.step == b.step == 3 and a.b1p == b.b1p and a.b2p == b.b2p
+    untouched = sorted(set(range(n_rows)) - touched)
+    assert untouched, "the test wants some rows nobody pushed"
+    got = a.var.reshape(n_rows, d)[untouched]
+    assert np.array_equal(got, init.reshape(n_rows, d)[untouched])
+    # hand case (SGD, SUM): row 1 pushed by workers 0 and 2 -> var -= lr * (g0 + g2)
+    if opt == o.SGD and mode == o.SUM:
+        s = o.Shard(3 * 2, o.SGD, lr=0.5)
+        s.var[:] = 1.0
+        o.rows_round(s, 2, [np.array([1]), np.array([0]), np.array([1, 2])],
+                     [np.array([[0.2, 0.4]], F), np.array([[1.0, 1.0]], F),
+                      np.array([[0.6, 0.0], [2.0, 2.0]], F)], o.SUM)
+        want = np.array([[0.5, 0.5], [1 - 0.5 * F(0.2 + F(0.6)), 1 - 0.5 * 0.4], [0.0, 0.0]], F)
+        np.testing.assert_allclose(s.var.reshape(3, 2), want, rtol=1e-6)
